@@ -1,0 +1,208 @@
+/*
+ * ipsolver_b200 -- C ABI of the B200-native projected-CG / null-space-projection
+ * hot path (fp64, sm_100a).
+ *
+ * The reference (antonior92/ip-nonlinear-solver) is pure Python and has no FFI;
+ * its seam for this path is two Python signatures plus the scipy
+ * LinearOperator protocol.  Every entry point below
+ * names the reference interface it stands in for; the ctypes binding a
+ * maintainer would add is shown in INTEGRATION.md and shipped in
+ * ip-nonlinear-solver_b200/ipsolver_b200/_cabi.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all host vectors are contiguous fp64;
+ *   - every function returns an ipb_status (0 = ok); ipb_last_error() gives
+ *     the message of the last failure on that context;
+ *   - host buffers are never retained past the call that received them;
+ *   - handles (ipb_csr, ipb_hess, ipb_proj, ipb_vec) are opaque device objects
+ *     owned by the context that created them.
+ */
+#ifndef IPSOLVER_B200_H
+#define IPSOLVER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ipb_ctx ipb_ctx;
+typedef struct ipb_csr ipb_csr;
+typedef struct ipb_hess ipb_hess;
+typedef struct ipb_proj ipb_proj;
+typedef struct ipb_vec ipb_vec;
+
+typedef enum {
+    IPB_OK = 0,
+    IPB_ERR_INVALID = 1,          /* bad argument                                  */
+    IPB_ERR_CUDA = 2,             /* CUDA runtime failure                          */
+    IPB_ERR_TR_INFEASIBLE = 3,    /* qp_subproblem.py:516-517 (ValueError)         */
+    IPB_ERR_NEG_CURVATURE = 4,    /* qp_subproblem.py:559-562 (ValueError)         */
+    IPB_ERR_INNER_SOLVE = 5,      /* inner CG on A A' broke down / did not converge */
+    IPB_ERR_NOMEM = 6,
+    IPB_ERR_COMM = 7              /* multi-GPU exchange failure / timeout          */
+} ipb_status;
+
+/* Result of one projected-CG solve: the reference's ``info`` dict
+ * (qp_subproblem.py:639-643) plus counters of the inner work. */
+typedef struct {
+    int64_t niter;            /* info['niter']                                   */
+    int32_t stop_cond;        /* info['stop_cond'] 1..4                          */
+    int32_t hits_boundary;    /* info['hits_boundary']                           */
+    int32_t status;           /* ipb_status raised inside the kernel             */
+    int32_t n_allvecs;        /* vectors stored when return_all was requested    */
+    int64_t inner_iters;      /* CG iterations on A A' summed over all solves    */
+    int64_t n_solves;         /* number of (A A')^-1 solves                      */
+    int64_t n_refinements;    /* iterative-refinement rounds (projections.py:72) */
+    int64_t n_spmv_h;         /* H products                                      */
+    double  max_orth;         /* largest orthogonality() accepted                */
+    double  tol_used;         /* tolerance actually used (default rule :530)     */
+    double  kernel_ms;        /* device time of the solve kernel (CUDA events)   */
+} ipb_pcg_info;
+
+/* Counters of one projector application (Z, LS or Y). */
+typedef struct {
+    int64_t inner_iters;
+    int64_t n_solves;
+    int64_t n_refinements;
+    int32_t status;
+    int32_t reserved;
+    double  orth;             /* orthogonality(A, z) of the returned z (Z only)  */
+    double  kernel_ms;
+} ipb_proj_info;
+
+/* ---- context ---------------------------------------------------------- */
+/* One context per process and GPU.  device = CUDA ordinal. */
+int ipb_ctx_create(int device, ipb_ctx **out);
+int ipb_ctx_destroy(ipb_ctx *ctx);
+const char *ipb_last_error(const ipb_ctx *ctx);
+/* grid of the persistent kernels (blocks, threads/block, SM count). */
+int ipb_ctx_grid(const ipb_ctx *ctx, int *blocks, int *threads, int *sms);
+/* cumulative count of kernels launched by this library on this context. */
+int64_t ipb_ctx_launches(const ipb_ctx *ctx);
+int ipb_ctx_sync(ipb_ctx *ctx);
+
+/* ---- CSR matrices (A, the sparse part of H) ---------------------------- */
+/* Replaces scipy.sparse.csr_matrix as consumed by A.dot / A.T.dot / H.dot
+ * (csr_matvec call sites: projections.py:52,66,67,76,77,84,88;
+ * qp_subproblem.py:376,379,410; equality_constrained_sqp.py:86,125,138,140).
+ * index_bytes is 4 or 8 (the barrier Jacobian arrives with int64 indices,
+ * tr_interior_point.py:184-193).  with_transpose builds the explicit CSR of
+ * the transpose on the device (deterministic A'.y, no atomics). */
+int ipb_csr_create(ipb_ctx *ctx, int64_t rows, int64_t cols, int64_t nnz,
+                   const void *indptr, const void *indices, int index_bytes,
+                   const double *data, int with_transpose, ipb_csr **out);
+/* same sparsity pattern, new values (one upload per outer iteration). */
+int ipb_csr_update_values(ipb_ctx *ctx, ipb_csr *m, const double *data);
+int ipb_csr_destroy(ipb_ctx *ctx, ipb_csr *m);
+/* y = A x (host vectors).  */
+int ipb_csr_matvec(ipb_ctx *ctx, const ipb_csr *m, const double *x, double *y);
+/* x = A' y (host vectors); needs with_transpose. */
+int ipb_csr_rmatvec(ipb_ctx *ctx, const ipb_csr *m, const double *y, double *x);
+/* device-resident variants */
+int ipb_csr_matvec_dev(ipb_ctx *ctx, const ipb_csr *m, const ipb_vec *x, ipb_vec *y);
+int ipb_csr_rmatvec_dev(ipb_ctx *ctx, const ipb_csr *m, const ipb_vec *y, ipb_vec *x);
+/* ||A||_F  (scipy.sparse.linalg.norm(A, 'fro'), projections.py:44) */
+int ipb_csr_fro_norm(ipb_ctx *ctx, const ipb_csr *m, double *out);
+
+/* ---- Lagrangian Hessian operator --------------------------------------- */
+/* Replaces the closure-backed LinearOperator of
+ * _canonical_constraint.py:119-139 and the barrier version
+ * tr_interior_point.py:222-241:
+ *     H v = [ (S + D) v_x ; diag_tail * v_s ]
+ * S: CSR n_x x n_x (may be NULL), D: dense row-major n_x x n_x (may be NULL),
+ * diag_tail: n - n_x entries (S Hs S, tr_interior_point.py:206-220). */
+int ipb_hess_create(ipb_ctx *ctx, int64_t n, int64_t n_x, ipb_hess **out);
+int ipb_hess_set_csr(ipb_ctx *ctx, ipb_hess *h, ipb_csr *s);       /* borrowed */
+int ipb_hess_set_dense(ipb_ctx *ctx, ipb_hess *h, const double *d); /* copied  */
+int ipb_hess_set_diag_tail(ipb_ctx *ctx, ipb_hess *h, const double *diag);
+int ipb_hess_destroy(ipb_ctx *ctx, ipb_hess *h);
+int ipb_hess_matvec(ipb_ctx *ctx, const ipb_hess *h, const double *x, double *y);
+int ipb_hess_matvec_dev(ipb_ctx *ctx, const ipb_hess *h, const ipb_vec *x, ipb_vec *y);
+
+/* ---- projectors --------------------------------------------------------- */
+/* Replaces projections(A, method, orth_tol, max_refin, tol) for sparse A
+ * (projections.py:290-406; NormalEquation :58-90, AugmentedSystem :93-172).
+ * (A A')^-1 is applied by a conjugate-gradient iteration on the row-normalised
+ * A (Jacobi-preconditioned CG on A A'), never by a factorisation.  A is
+ * borrowed and must have been created with_transpose. */
+int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int max_refin,
+                    double inner_rtol, int inner_maxit, ipb_proj **out);
+/* call after ipb_csr_update_values(A): refreshes row norms, ||A||_F, A'. */
+int ipb_proj_refresh(ipb_ctx *ctx, ipb_proj *p);
+int ipb_proj_destroy(ipb_ctx *ctx, ipb_proj *p);
+/* Z: z = x - A'(AA')^-1 A x with refinement (null_space closures :65-80, :114-142) */
+int ipb_proj_null_space(ipb_ctx *ctx, ipb_proj *p, const double *x, double *z,
+                        ipb_proj_info *info);
+/* LS: v = (AA')^-1 A x  (:83-84, :148-156) */
+int ipb_proj_least_squares(ipb_ctx *ctx, ipb_proj *p, const double *x, double *v,
+                           ipb_proj_info *info);
+/* Y: y = A'(AA')^-1 b  (:87-88, :162-170) */
+int ipb_proj_row_space(ipb_ctx *ctx, ipb_proj *p, const double *b, double *y,
+                       ipb_proj_info *info);
+int ipb_proj_null_space_dev(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x, ipb_vec *z,
+                            ipb_proj_info *info);
+int ipb_proj_least_squares_dev(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x, ipb_vec *v,
+                               ipb_proj_info *info);
+int ipb_proj_row_space_dev(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *b, ipb_vec *y,
+                           ipb_proj_info *info);
+/* orthogonality(A, g) = ||A g|| / (||A||_F ||g||)  (projections.py:23-55) */
+int ipb_orthogonality(ipb_ctx *ctx, ipb_proj *p, const double *g, double *out);
+
+/* ---- the trust-region EQP solve ----------------------------------------- */
+/* Replaces projected_cg(H, c, Z, Y, b, trust_radius, lb, ub, tol, max_iter,
+ * max_infeasible_iter, return_all) (qp_subproblem.py:416-643).
+ *   lb / ub may be NULL (= -inf / +inf); trust_radius may be +inf;
+ *   tol < 0 or NaN selects the default rule (:529-530);
+ *   max_iter / max_infeasible_iter < 0 select the default n - m (:537-542);
+ *   allvecs (may be NULL) receives up to allvecs_cap iterates of n doubles
+ *   (return_all; :508-509, :618-619), info->n_allvecs says how many.
+ * Returns IPB_ERR_TR_INFEASIBLE / IPB_ERR_NEG_CURVATURE where the reference
+ * raises ValueError. */
+int ipb_projected_cg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P,
+                     const double *c, const double *b, double trust_radius,
+                     const double *lb, const double *ub, double tol,
+                     int64_t max_iter, int64_t max_infeasible_iter,
+                     double *x, double *allvecs, int64_t allvecs_cap,
+                     ipb_pcg_info *info);
+/* inputs and result resident in HBM (only ``info`` crosses PCIe). */
+int ipb_projected_cg_dev(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P,
+                         const ipb_vec *c, const ipb_vec *b, double trust_radius,
+                         const ipb_vec *lb, const ipb_vec *ub, double tol,
+                         int64_t max_iter, int64_t max_infeasible_iter,
+                         ipb_vec *x, ipb_pcg_info *info);
+
+/* Replaces modified_dogleg(A, Y, b, trust_radius, lb, ub)
+ * (qp_subproblem.py:320-413).  lb / ub may be NULL. */
+int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b,
+                        double trust_radius, const double *lb, const double *ub,
+                        double *x, ipb_proj_info *info);
+
+/* Replaces box_sphere_intersections(z, d, lb, ub, trust_radius, entire_line)
+ * (qp_subproblem.py:237-303); with lb = ub = NULL it is sphere_intersections
+ * (:66-149), with trust_radius = +inf it is box_intersections (:152-234, the
+ * form the SQP second-order correction calls, equality_constrained_sqp.py:177). */
+int ipb_box_sphere_intersections(ipb_ctx *ctx, int64_t n, const double *z,
+                                 const double *d, const double *lb, const double *ub,
+                                 double trust_radius, int entire_line, double *ta,
+                                 double *tb, int *intersect);
+
+/* ---- device vectors ------------------------------------------------------ */
+int ipb_vec_create(ipb_ctx *ctx, int64_t len, ipb_vec **out);
+int ipb_vec_destroy(ipb_ctx *ctx, ipb_vec *v);
+int ipb_vec_upload(ipb_ctx *ctx, ipb_vec *v, const double *host);
+int ipb_vec_download(ipb_ctx *ctx, const ipb_vec *v, double *host);
+int64_t ipb_vec_len(const ipb_vec *v);
+void *ipb_vec_ptr(ipb_vec *v);   /* raw device pointer (for torch interop) */
+
+/* ---- measurement helpers (bench.py) -------------------------------------- */
+/* Runs ``iters`` inner CG iterations on A A' (fixed count, no convergence
+ * test) starting from rhs = A x; returns device milliseconds.  This is the
+ * dominant loop of the path, timed in isolation. */
+int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x,
+                               int iters, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPSOLVER_B200_H */

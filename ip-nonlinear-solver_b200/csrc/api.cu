@@ -1,0 +1,883 @@
+// Host side of the C ABI declared in include/ipsolver_b200.h.
+// Owns device memory, builds the transposed / row-normalised copies of A,
+// and launches the persistent cooperative kernels of device.cuh.
+#include "device.cuh"
+#include "../../include/ipsolver_b200.h"
+
+#include <cub/cub.cuh>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace ipb;
+
+// ------------------------------------------------------------------ objects
+struct ipb_vec {
+    double *d = nullptr;
+    int64_t len = 0;
+};
+
+struct ipb_csr {
+    int rows = 0, cols = 0;
+    int64_t nnz = 0;
+    int *rowptr = nullptr, *col = nullptr;
+    double *val = nullptr;
+    int rpt = 1;
+    bool has_t = false;
+    int *t_rowptr = nullptr, *t_col = nullptr, *perm = nullptr;
+    double *t_val = nullptr;
+    int t_rpt = 1;
+};
+
+struct ipb_hess {
+    int64_t n = 0, nx = 0;
+    ipb_csr *S = nullptr;
+    double *D = nullptr;
+    double *tail = nullptr;
+};
+
+struct ipb_proj {
+    ipb_csr *A = nullptr;
+    double *nval = nullptr, *nt_val = nullptr;     // row-normalised A and A'
+    double *dscale = nullptr, *dnorm2 = nullptr;
+    double fro = 0.0;
+    double orth_tol = 1e-12, rtol = 1e-13;
+    int max_refin = 3, maxit = 1000;
+    double *v = nullptr, *r = nullptr, *w = nullptr, *p = nullptr, *s = nullptr,
+           *rhs = nullptr, *t = nullptr;
+};
+
+struct ipb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sms = 0, blocks = 0;
+    unsigned *barrier = nullptr;
+    double *partials = nullptr;
+    int *abort_flag = nullptr;
+    void *d_result = nullptr;          // device result struct (256 B)
+    void *h_result = nullptr;          // pinned mirror
+    // workspace for n- and m- sized temporaries of the solve kernels
+    double *ws = nullptr;
+    size_t ws_len = 0;
+    double *stage = nullptr;           // device staging for host-vector calls
+    size_t stage_len = 0;
+    void *cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    int64_t launches = 0;
+    std::string err;
+};
+
+#define IPB_FAIL(ctx, code, ...)                                              \
+    do {                                                                      \
+        char _b[512];                                                         \
+        snprintf(_b, sizeof _b, __VA_ARGS__);                                 \
+        (ctx)->err = _b;                                                      \
+        return (code);                                                        \
+    } while (0)
+
+#define CU(ctx, call)                                                         \
+    do {                                                                      \
+        cudaError_t _e = (call);                                              \
+        if (_e != cudaSuccess)                                                \
+            IPB_FAIL(ctx, IPB_ERR_CUDA, "%s failed: %s (%s:%d)", #call,       \
+                     cudaGetErrorString(_e), __FILE__, __LINE__);             \
+    } while (0)
+
+#define CHECK(expr)                                                           \
+    do {                                                                      \
+        int _s = (expr);                                                      \
+        if (_s != IPB_OK) return _s;                                          \
+    } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+template <typename T>
+static int dalloc(ipb_ctx *ctx, T **p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    if (e != cudaSuccess)
+        IPB_FAIL(ctx, IPB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s",
+                 count * sizeof(T), cudaGetErrorString(e));
+    return IPB_OK;
+}
+
+static SyncView sync_view(const ipb_ctx *ctx) {
+    SyncView s;
+    s.barrier = ctx->barrier;
+    s.partials = ctx->partials;
+    s.abort_flag = ctx->abort_flag;
+    return s;
+}
+
+static CsrView csr_view(const ipb_csr *m, const double *val_override = nullptr) {
+    CsrView v;
+    v.rows = m->rows; v.cols = m->cols; v.rpt = m->rpt;
+    v.rowptr = m->rowptr; v.col = m->col;
+    v.val = val_override ? val_override : m->val;
+    return v;
+}
+
+static CsrView csr_view_t(const ipb_csr *m, const double *val_override = nullptr) {
+    CsrView v;
+    v.rows = m->cols; v.cols = m->rows; v.rpt = m->t_rpt;
+    v.rowptr = m->t_rowptr; v.col = m->t_col;
+    v.val = val_override ? val_override : m->t_val;
+    return v;
+}
+
+static int pick_rpt(int64_t rows, int64_t nnz) {
+    if (rows <= 0) return 1;
+    double avg = std::max(1e-9, (double)nnz / (double)rows);
+    int rpt = (int)std::floor(0.92 * CHUNK / (avg * THREADS));
+    return std::max(1, std::min(RPT_MAX, rpt));
+}
+
+// number of CTAs for a launch working on ``work`` items: enough to fill the
+// machine for large problems, a handful for tiny ones (cheap barriers).
+static int grid_for(const ipb_ctx *ctx, int64_t work) {
+    int64_t want = (work + THREADS * 4 - 1) / (THREADS * 4);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(ctx->blocks, want));
+}
+
+template <typename Args>
+static int launch_coop(ipb_ctx *ctx, void (*kernel)(const Args), const Args &args,
+                       int grid, float *ms) {
+    CU(ctx, cudaMemsetAsync(ctx->barrier, 0, sizeof(unsigned), ctx->stream));
+    void *params[] = {(void *)&args};
+    if (ms) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(ctx, cudaLaunchCooperativeKernel((void *)kernel, dim3(grid), dim3(THREADS),
+                                        params, 0, ctx->stream));
+    ctx->launches += 1;
+    if (ms) {
+        CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(ctx, cudaEventSynchronize(ctx->ev1));
+        CU(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    }
+    return IPB_OK;
+}
+
+static int ensure_ws(ipb_ctx *ctx, size_t len) {
+    if (ctx->ws_len >= len) return IPB_OK;
+    if (ctx->ws) cudaFree(ctx->ws);
+    ctx->ws = nullptr; ctx->ws_len = 0;
+    CHECK(dalloc(ctx, &ctx->ws, len));
+    ctx->ws_len = len;
+    return IPB_OK;
+}
+
+static int ensure_stage(ipb_ctx *ctx, size_t len) {
+    if (ctx->stage_len >= len) return IPB_OK;
+    if (ctx->stage) cudaFree(ctx->stage);
+    ctx->stage = nullptr; ctx->stage_len = 0;
+    CHECK(dalloc(ctx, &ctx->stage, len));
+    ctx->stage_len = len;
+    return IPB_OK;
+}
+
+static int ensure_cub(ipb_ctx *ctx, size_t bytes) {
+    if (ctx->cub_tmp_bytes >= bytes) return IPB_OK;
+    if (ctx->cub_tmp) cudaFree(ctx->cub_tmp);
+    ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0;
+    char *p;
+    CHECK(dalloc(ctx, &p, bytes));
+    ctx->cub_tmp = p; ctx->cub_tmp_bytes = bytes;
+    return IPB_OK;
+}
+
+// ------------------------------------------------------------------ context
+extern "C" int ipb_ctx_create(int device, ipb_ctx **out) {
+    if (!out) return IPB_ERR_INVALID;
+    *out = nullptr;
+    ipb_ctx *ctx = new ipb_ctx();
+    *out = ctx;          // returned even on failure so the message is readable
+    ctx->device = device;
+    CU(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(ctx, cudaGetDeviceProperties(&prop, device));
+    if (!prop.cooperativeLaunch)
+        IPB_FAIL(ctx, IPB_ERR_CUDA, "device %d lacks cooperative launch", device);
+    ctx->sms = prop.multiProcessorCount;
+    CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(ctx, cudaEventCreate(&ctx->ev0));
+    CU(ctx, cudaEventCreate(&ctx->ev1));
+    int occ = 0, o;
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_projected_cg, THREADS, 0));
+    occ = o;
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_projector, THREADS, 0));
+    occ = std::min(occ, o);
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dogleg, THREADS, 0));
+    occ = std::min(occ, o);
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_matvec, THREADS, 0));
+    occ = std::min(occ, o);
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_intersect, THREADS, 0));
+    occ = std::min(occ, o);
+    if (occ < 1) IPB_FAIL(ctx, IPB_ERR_CUDA, "kernels do not fit on an SM");
+    int per_sm = occ;
+    const char *env = getenv("IPB_BLOCKS_PER_SM");
+    if (env && atoi(env) > 0) per_sm = std::min(occ, atoi(env));
+    ctx->blocks = std::min(MAX_GRID, per_sm * ctx->sms);
+    CHECK(dalloc(ctx, &ctx->barrier, 1));
+    CHECK(dalloc(ctx, &ctx->partials, (size_t)NSLOT * MAX_GRID));
+    CHECK(dalloc(ctx, &ctx->abort_flag, 1));
+    CU(ctx, cudaMemset(ctx->barrier, 0, sizeof(unsigned)));
+    CU(ctx, cudaMemset(ctx->abort_flag, 0, sizeof(int)));
+    CU(ctx, cudaMalloc(&ctx->d_result, 256));
+    CU(ctx, cudaMallocHost(&ctx->h_result, 256));
+    return IPB_OK;
+}
+
+extern "C" int ipb_ctx_destroy(ipb_ctx *ctx) {
+    if (!ctx) return IPB_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->barrier); cudaFree(ctx->partials); cudaFree(ctx->abort_flag);
+    cudaFree(ctx->d_result); cudaFreeHost(ctx->h_result);
+    cudaFree(ctx->ws); cudaFree(ctx->stage); cudaFree(ctx->cub_tmp);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return IPB_OK;
+}
+
+extern "C" const char *ipb_last_error(const ipb_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : "null context";
+}
+
+extern "C" int ipb_ctx_grid(const ipb_ctx *ctx, int *blocks, int *threads, int *sms) {
+    if (!ctx) return IPB_ERR_INVALID;
+    if (blocks) *blocks = ctx->blocks;
+    if (threads) *threads = THREADS;
+    if (sms) *sms = ctx->sms;
+    return IPB_OK;
+}
+
+extern "C" int64_t ipb_ctx_launches(const ipb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ipb_ctx_sync(ipb_ctx *ctx) {
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+// ------------------------------------------------------------------ vectors
+extern "C" int ipb_vec_create(ipb_ctx *ctx, int64_t len, ipb_vec **out) {
+    if (!ctx || !out || len < 0) return IPB_ERR_INVALID;
+    ipb_vec *v = new ipb_vec();
+    v->len = len;
+    int s = dalloc(ctx, &v->d, (size_t)len);
+    if (s != IPB_OK) { delete v; return s; }
+    *out = v;
+    return IPB_OK;
+}
+extern "C" int ipb_vec_destroy(ipb_ctx *ctx, ipb_vec *v) {
+    (void)ctx;
+    if (v) { cudaFree(v->d); delete v; }
+    return IPB_OK;
+}
+extern "C" int ipb_vec_upload(ipb_ctx *ctx, ipb_vec *v, const double *host) {
+    CU(ctx, cudaMemcpyAsync(v->d, host, v->len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+extern "C" int ipb_vec_download(ipb_ctx *ctx, const ipb_vec *v, double *host) {
+    CU(ctx, cudaMemcpyAsync(host, v->d, v->len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+extern "C" int64_t ipb_vec_len(const ipb_vec *v) { return v ? v->len : 0; }
+extern "C" void *ipb_vec_ptr(ipb_vec *v) { return v ? v->d : nullptr; }
+
+// ------------------------------------------------------------------ CSR
+static int build_transpose(ipb_ctx *ctx, ipb_csr *m) {
+    const int64_t nnz = m->nnz;
+    const int TB = 256;
+    CHECK(dalloc(ctx, &m->t_rowptr, (size_t)m->cols + 1));
+    CHECK(dalloc(ctx, &m->t_col, (size_t)nnz));
+    CHECK(dalloc(ctx, &m->t_val, (size_t)nnz));
+    CHECK(dalloc(ctx, &m->perm, (size_t)nnz));
+    CU(ctx, cudaMemsetAsync(m->t_rowptr, 0, ((size_t)m->cols + 1) * sizeof(int), ctx->stream));
+    if (nnz > 0) {
+        int *rowidx, *iota, *keys_out;
+        CHECK(dalloc(ctx, &rowidx, (size_t)nnz));
+        CHECK(dalloc(ctx, &iota, (size_t)nnz));
+        CHECK(dalloc(ctx, &keys_out, (size_t)nnz));
+        k_expand_rows<<<cdiv(m->rows, TB), TB, 0, ctx->stream>>>(m->rows, m->rowptr, rowidx);
+        k_iota<<<cdiv(nnz, TB), TB, 0, ctx->stream>>>(nnz, iota);
+        k_count_cols<<<cdiv(nnz, TB), TB, 0, ctx->stream>>>(nnz, m->col, m->t_rowptr);
+        ctx->launches += 3;
+        int bits = 1;
+        while ((1ll << bits) < (int64_t)m->cols && bits < 31) ++bits;
+        size_t tmp = 0;
+        CU(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, m->col, keys_out, iota, m->perm,
+                                                (int)nnz, 0, bits, ctx->stream));
+        CHECK(ensure_cub(ctx, tmp));
+        CU(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp, tmp, m->col, keys_out, iota, m->perm,
+                                                (int)nnz, 0, bits, ctx->stream));
+        // t_col[k] = row of the k-th entry in column order
+        k_gather_int<<<cdiv(nnz, TB), TB, 0, ctx->stream>>>(nnz, m->perm, rowidx, m->t_col);
+        k_gather<<<cdiv(nnz, TB), TB, 0, ctx->stream>>>(nnz, m->perm, m->val, m->t_val);
+        ctx->launches += 2;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(rowidx); cudaFree(iota); cudaFree(keys_out);
+    }
+    // rowptr of the transpose: inclusive scan of the shifted column counts
+    {
+        size_t tmp = 0;
+        CU(ctx, cub::DeviceScan::InclusiveSum(nullptr, tmp, m->t_rowptr, m->t_rowptr,
+                                              m->cols + 1, ctx->stream));
+        CHECK(ensure_cub(ctx, tmp));
+        CU(ctx, cub::DeviceScan::InclusiveSum(ctx->cub_tmp, tmp, m->t_rowptr, m->t_rowptr,
+                                              m->cols + 1, ctx->stream));
+    }
+    m->t_rpt = pick_rpt(m->cols, nnz);
+    m->has_t = true;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+extern "C" int ipb_csr_create(ipb_ctx *ctx, int64_t rows, int64_t cols, int64_t nnz,
+                              const void *indptr, const void *indices, int index_bytes,
+                              const double *data, int with_transpose, ipb_csr **out) {
+    if (!ctx || !out) return IPB_ERR_INVALID;
+    if (rows < 0 || cols < 0 || nnz < 0 || (index_bytes != 4 && index_bytes != 8))
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "ipb_csr_create: bad shape or index width");
+    if (rows >= (1ll << 31) - 1 || cols >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1)
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "ipb_csr_create: dimensions exceed int32 per-GPU limit");
+    CU(ctx, cudaSetDevice(ctx->device));
+    ipb_csr *m = new ipb_csr();
+    m->rows = (int)rows; m->cols = (int)cols; m->nnz = nnz;
+    m->rpt = pick_rpt(rows, nnz);
+    int s;
+    if ((s = dalloc(ctx, &m->rowptr, (size_t)rows + 1)) != IPB_OK) return s;
+    if ((s = dalloc(ctx, &m->col, (size_t)nnz)) != IPB_OK) return s;
+    if ((s = dalloc(ctx, &m->val, (size_t)nnz)) != IPB_OK) return s;
+    if (index_bytes == 4) {
+        CU(ctx, cudaMemcpyAsync(m->rowptr, indptr, ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (nnz) CU(ctx, cudaMemcpyAsync(m->col, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        long long *tmp;
+        size_t cnt = (size_t)std::max<int64_t>(rows + 1, nnz);
+        if ((s = dalloc(ctx, &tmp, cnt)) != IPB_OK) return s;
+        CU(ctx, cudaMemcpyAsync(tmp, indptr, ((size_t)rows + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        k_narrow_i64<<<cdiv(rows + 1, 256), 256, 0, ctx->stream>>>(rows + 1, tmp, m->rowptr);
+        ctx->launches += 1;
+        if (nnz) {
+            CU(ctx, cudaMemcpyAsync(tmp, indices, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+            k_narrow_i64<<<cdiv(nnz, 256), 256, 0, ctx->stream>>>(nnz, tmp, m->col);
+            ctx->launches += 1;
+        }
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp);
+    }
+    if (nnz) CU(ctx, cudaMemcpyAsync(m->val, data, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (rows == 0) CU(ctx, cudaMemsetAsync(m->rowptr, 0, sizeof(int), ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (with_transpose) {
+        s = build_transpose(ctx, m);
+        if (s != IPB_OK) return s;
+    }
+    *out = m;
+    return IPB_OK;
+}
+
+extern "C" int ipb_csr_update_values(ipb_ctx *ctx, ipb_csr *m, const double *data) {
+    if (!ctx || !m) return IPB_ERR_INVALID;
+    if (m->nnz) {
+        CU(ctx, cudaMemcpyAsync(m->val, data, (size_t)m->nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (m->has_t) {
+            k_gather<<<cdiv(m->nnz, 256), 256, 0, ctx->stream>>>(m->nnz, m->perm, m->val, m->t_val);
+            ctx->launches += 1;
+        }
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+extern "C" int ipb_csr_destroy(ipb_ctx *ctx, ipb_csr *m) {
+    (void)ctx;
+    if (!m) return IPB_OK;
+    cudaFree(m->rowptr); cudaFree(m->col); cudaFree(m->val);
+    cudaFree(m->t_rowptr); cudaFree(m->t_col); cudaFree(m->t_val); cudaFree(m->perm);
+    delete m;
+    return IPB_OK;
+}
+
+static int run_matvec(ipb_ctx *ctx, const CsrView &M, const double *dx, double *dy) {
+    MatvecArgs a;
+    memset(&a, 0, sizeof a);
+    a.kind = 0; a.M = M; a.S = sync_view(ctx); a.x = dx; a.y = dy;
+    int grid = grid_for(ctx, std::max<int64_t>(M.rows, 1) * 4);
+    return launch_coop(ctx, k_matvec, a, grid, nullptr);
+}
+
+static int host_in_out(ipb_ctx *ctx, int64_t nin, int64_t nout, const double *hin,
+                       double **din, double **dout) {
+    CHECK(ensure_stage(ctx, (size_t)(nin + nout)));
+    *din = ctx->stage; *dout = ctx->stage + nin;
+    if (nin) CU(ctx, cudaMemcpyAsync(*din, hin, (size_t)nin * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return IPB_OK;
+}
+
+static int host_out(ipb_ctx *ctx, int64_t nout, const double *dout, double *hout) {
+    if (nout) CU(ctx, cudaMemcpyAsync(hout, dout, (size_t)nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+extern "C" int ipb_csr_matvec(ipb_ctx *ctx, const ipb_csr *m, const double *x, double *y) {
+    if (!ctx || !m) return IPB_ERR_INVALID;
+    double *dx, *dy;
+    CHECK(host_in_out(ctx, m->cols, m->rows, x, &dx, &dy));
+    CHECK(run_matvec(ctx, csr_view(m), dx, dy));
+    return host_out(ctx, m->rows, dy, y);
+}
+
+extern "C" int ipb_csr_rmatvec(ipb_ctx *ctx, const ipb_csr *m, const double *y, double *x) {
+    if (!ctx || !m) return IPB_ERR_INVALID;
+    if (!m->has_t) IPB_FAIL(ctx, IPB_ERR_INVALID, "matrix was created without its transpose");
+    double *dy, *dx;
+    CHECK(host_in_out(ctx, m->rows, m->cols, y, &dy, &dx));
+    CHECK(run_matvec(ctx, csr_view_t(m), dy, dx));
+    return host_out(ctx, m->cols, dx, x);
+}
+
+extern "C" int ipb_csr_matvec_dev(ipb_ctx *ctx, const ipb_csr *m, const ipb_vec *x, ipb_vec *y) {
+    if (!ctx || !m || !x || !y || x->len != m->cols || y->len != m->rows)
+        return IPB_ERR_INVALID;
+    return run_matvec(ctx, csr_view(m), x->d, y->d);
+}
+
+extern "C" int ipb_csr_rmatvec_dev(ipb_ctx *ctx, const ipb_csr *m, const ipb_vec *y, ipb_vec *x) {
+    if (!ctx || !m || !x || !y || x->len != m->cols || y->len != m->rows || !m->has_t)
+        return IPB_ERR_INVALID;
+    return run_matvec(ctx, csr_view_t(m), y->d, x->d);
+}
+
+static int device_sum(ipb_ctx *ctx, const double *d, int64_t n, double *out) {
+    double *dres = (double *)ctx->d_result;
+    size_t tmp = 0;
+    CU(ctx, cub::DeviceReduce::Sum(nullptr, tmp, d, dres, (int)n, ctx->stream));
+    CHECK(ensure_cub(ctx, tmp));
+    CU(ctx, cub::DeviceReduce::Sum(ctx->cub_tmp, tmp, d, dres, (int)n, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out, dres, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+extern "C" int ipb_csr_fro_norm(ipb_ctx *ctx, const ipb_csr *m, double *out) {
+    if (!ctx || !m || !out) return IPB_ERR_INVALID;
+    double *d2, *ds;
+    CHECK(dalloc(ctx, &d2, (size_t)m->rows));
+    CHECK(dalloc(ctx, &ds, (size_t)m->rows));
+    double s = 0.0;
+    if (m->rows > 0) {
+        k_row_norms<<<cdiv(m->rows, 256), 256, 0, ctx->stream>>>(m->rows, m->rowptr, m->val, d2, ds);
+        ctx->launches += 1;
+        CHECK(device_sum(ctx, d2, m->rows, &s));
+    }
+    cudaFree(d2); cudaFree(ds);
+    *out = std::sqrt(s);
+    return IPB_OK;
+}
+
+// ------------------------------------------------------------------ Hessian
+extern "C" int ipb_hess_create(ipb_ctx *ctx, int64_t n, int64_t n_x, ipb_hess **out) {
+    if (!ctx || !out || n < 0 || n_x < 0 || n_x > n) return IPB_ERR_INVALID;
+    ipb_hess *h = new ipb_hess();
+    h->n = n; h->nx = n_x;
+    *out = h;
+    return IPB_OK;
+}
+extern "C" int ipb_hess_set_csr(ipb_ctx *ctx, ipb_hess *h, ipb_csr *s) {
+    if (!ctx || !h) return IPB_ERR_INVALID;
+    if (s && (s->rows != h->nx || s->cols != h->nx))
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "Hessian CSR term must be n_x by n_x");
+    h->S = s;
+    return IPB_OK;
+}
+extern "C" int ipb_hess_set_dense(ipb_ctx *ctx, ipb_hess *h, const double *d) {
+    if (!ctx || !h) return IPB_ERR_INVALID;
+    if (!d) { cudaFree(h->D); h->D = nullptr; return IPB_OK; }
+    size_t cnt = (size_t)h->nx * (size_t)h->nx;
+    if (!h->D) CHECK(dalloc(ctx, &h->D, cnt));
+    CU(ctx, cudaMemcpyAsync(h->D, d, cnt * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+extern "C" int ipb_hess_set_diag_tail(ipb_ctx *ctx, ipb_hess *h, const double *diag) {
+    if (!ctx || !h) return IPB_ERR_INVALID;
+    if (!diag) { cudaFree(h->tail); h->tail = nullptr; return IPB_OK; }
+    size_t cnt = (size_t)(h->n - h->nx);
+    if (!h->tail) CHECK(dalloc(ctx, &h->tail, cnt));
+    if (cnt) CU(ctx, cudaMemcpyAsync(h->tail, diag, cnt * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+extern "C" int ipb_hess_destroy(ipb_ctx *ctx, ipb_hess *h) {
+    (void)ctx;
+    if (!h) return IPB_OK;
+    cudaFree(h->D); cudaFree(h->tail);
+    delete h;
+    return IPB_OK;
+}
+
+static HessView hess_view(const ipb_hess *h) {
+    HessView v;
+    memset(&v, 0, sizeof v);
+    v.n = (int)h->n; v.nx = (int)h->nx;
+    v.has_csr = h->S != nullptr;
+    v.has_dense = h->D != nullptr;
+    v.has_tail = h->tail != nullptr;
+    if (h->S) v.S = csr_view(h->S);
+    v.D = h->D; v.tail = h->tail;
+    return v;
+}
+
+static int run_hess(ipb_ctx *ctx, const ipb_hess *h, const double *dx, double *dy) {
+    MatvecArgs a;
+    memset(&a, 0, sizeof a);
+    a.kind = 1; a.H = hess_view(h); a.S = sync_view(ctx); a.x = dx; a.y = dy;
+    int64_t work = std::max<int64_t>(h->n * 4, h->D ? h->nx * h->nx / 8 : 0);
+    return launch_coop(ctx, k_matvec, a, grid_for(ctx, work), nullptr);
+}
+
+extern "C" int ipb_hess_matvec(ipb_ctx *ctx, const ipb_hess *h, const double *x, double *y) {
+    if (!ctx || !h) return IPB_ERR_INVALID;
+    double *dx, *dy;
+    CHECK(host_in_out(ctx, h->n, h->n, x, &dx, &dy));
+    CHECK(run_hess(ctx, h, dx, dy));
+    return host_out(ctx, h->n, dy, y);
+}
+extern "C" int ipb_hess_matvec_dev(ipb_ctx *ctx, const ipb_hess *h, const ipb_vec *x, ipb_vec *y) {
+    if (!ctx || !h || !x || !y || x->len != h->n || y->len != h->n) return IPB_ERR_INVALID;
+    return run_hess(ctx, h, x->d, y->d);
+}
+
+// ------------------------------------------------------------------ projector
+extern "C" int ipb_proj_refresh(ipb_ctx *ctx, ipb_proj *p) {
+    if (!ctx || !p) return IPB_ERR_INVALID;
+    ipb_csr *A = p->A;
+    double s = 0.0;
+    if (A->rows > 0) {
+        k_row_norms<<<cdiv(A->rows, 256), 256, 0, ctx->stream>>>(A->rows, A->rowptr, A->val,
+                                                                  p->dnorm2, p->dscale);
+        k_scale_rows<<<cdiv(A->rows, 256), 256, 0, ctx->stream>>>(A->rows, A->rowptr, A->val,
+                                                                   p->dscale, p->nval);
+        ctx->launches += 2;
+        if (A->nnz) {
+            k_gather<<<cdiv(A->nnz, 256), 256, 0, ctx->stream>>>(A->nnz, A->perm, p->nval, p->nt_val);
+            ctx->launches += 1;
+        }
+        CHECK(device_sum(ctx, p->dnorm2, A->rows, &s));
+    }
+    p->fro = std::sqrt(s);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+extern "C" int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int max_refin,
+                               double inner_rtol, int inner_maxit, ipb_proj **out) {
+    if (!ctx || !A || !out) return IPB_ERR_INVALID;
+    if (!A->has_t) IPB_FAIL(ctx, IPB_ERR_INVALID, "projector needs A created with_transpose");
+    ipb_proj *p = new ipb_proj();
+    p->A = A;
+    p->orth_tol = orth_tol; p->max_refin = max_refin;
+    p->rtol = inner_rtol > 0 ? inner_rtol : 1e-13;
+    p->maxit = inner_maxit > 0 ? inner_maxit : 1000;
+    size_t m = A->rows, n = A->cols, nnz = A->nnz;
+    CHECK(dalloc(ctx, &p->nval, nnz));
+    CHECK(dalloc(ctx, &p->nt_val, nnz));
+    CHECK(dalloc(ctx, &p->dscale, m));
+    CHECK(dalloc(ctx, &p->dnorm2, m));
+    CHECK(dalloc(ctx, &p->v, m)); CHECK(dalloc(ctx, &p->r, m)); CHECK(dalloc(ctx, &p->w, m));
+    CHECK(dalloc(ctx, &p->p, m)); CHECK(dalloc(ctx, &p->s, m)); CHECK(dalloc(ctx, &p->rhs, m));
+    CHECK(dalloc(ctx, &p->t, n));
+    CHECK(ipb_proj_refresh(ctx, p));
+    *out = p;
+    return IPB_OK;
+}
+
+extern "C" int ipb_proj_destroy(ipb_ctx *ctx, ipb_proj *p) {
+    (void)ctx;
+    if (!p) return IPB_OK;
+    cudaFree(p->nval); cudaFree(p->nt_val); cudaFree(p->dscale); cudaFree(p->dnorm2);
+    cudaFree(p->v); cudaFree(p->r); cudaFree(p->w); cudaFree(p->p); cudaFree(p->s);
+    cudaFree(p->rhs); cudaFree(p->t);
+    delete p;
+    return IPB_OK;
+}
+
+static ProjView proj_view(const ipb_proj *p) {
+    ProjView v;
+    memset(&v, 0, sizeof v);
+    v.m = p->A->rows; v.n = p->A->cols;
+    v.A = csr_view(p->A, p->nval);
+    v.At = csr_view_t(p->A, p->nt_val);
+    v.dscale = p->dscale; v.dnorm2 = p->dnorm2;
+    v.fro = p->fro; v.orth_tol = p->orth_tol; v.max_refin = p->max_refin;
+    v.rtol = p->rtol; v.maxit = p->maxit;
+    v.v = p->v; v.r = p->r; v.w = p->w; v.p = p->p; v.s = p->s; v.rhs = p->rhs; v.t = p->t;
+    return v;
+}
+
+static int proj_grid(const ipb_ctx *ctx, const ipb_proj *p) {
+    return grid_for(ctx, std::max<int64_t>(p->A->cols, 1) * 4);
+}
+
+static int run_proj(ipb_ctx *ctx, ipb_proj *p, int op, const double *din, double *dout,
+                    int fixed_iters, ipb_proj_info *info) {
+    ProjArgs a;
+    memset(&a, 0, sizeof a);
+    a.P = proj_view(p); a.S = sync_view(ctx); a.op = op; a.in = din; a.out = dout;
+    a.fixed_iters = fixed_iters;
+    a.result = (ProjArgs::Result *)ctx->d_result;
+    float ms = 0.f;
+    CHECK(launch_coop(ctx, k_projector, a, proj_grid(ctx, p), &ms));
+    ProjArgs::Result *h = (ProjArgs::Result *)ctx->h_result;
+    CU(ctx, cudaMemcpyAsync(h, ctx->d_result, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (info) {
+        info->inner_iters = h->inner_iters; info->n_solves = h->n_solves;
+        info->n_refinements = h->n_refinements; info->status = h->status;
+        info->reserved = 0; info->orth = h->orth; info->kernel_ms = ms;
+    }
+    if (h->status != 0)
+        IPB_FAIL(ctx, h->status, "inner CG on A A' broke down (status %d)", h->status);
+    return IPB_OK;
+}
+
+extern "C" int ipb_proj_null_space_dev(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x, ipb_vec *z,
+                                       ipb_proj_info *info) {
+    if (!ctx || !p || !x || !z || x->len != p->A->cols || z->len != p->A->cols) return IPB_ERR_INVALID;
+    return run_proj(ctx, p, 0, x->d, z->d, 0, info);
+}
+extern "C" int ipb_proj_least_squares_dev(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x, ipb_vec *v,
+                                          ipb_proj_info *info) {
+    if (!ctx || !p || !x || !v || x->len != p->A->cols || v->len != p->A->rows) return IPB_ERR_INVALID;
+    return run_proj(ctx, p, 1, x->d, v->d, 0, info);
+}
+extern "C" int ipb_proj_row_space_dev(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *b, ipb_vec *y,
+                                      ipb_proj_info *info) {
+    if (!ctx || !p || !b || !y || b->len != p->A->rows || y->len != p->A->cols) return IPB_ERR_INVALID;
+    return run_proj(ctx, p, 2, b->d, y->d, 0, info);
+}
+
+extern "C" int ipb_proj_null_space(ipb_ctx *ctx, ipb_proj *p, const double *x, double *z,
+                                   ipb_proj_info *info) {
+    if (!ctx || !p) return IPB_ERR_INVALID;
+    int64_t n = p->A->cols;
+    double *din, *dout;
+    CHECK(host_in_out(ctx, n, n, x, &din, &dout));
+    CHECK(run_proj(ctx, p, 0, din, dout, 0, info));
+    return host_out(ctx, n, dout, z);
+}
+extern "C" int ipb_proj_least_squares(ipb_ctx *ctx, ipb_proj *p, const double *x, double *v,
+                                      ipb_proj_info *info) {
+    if (!ctx || !p) return IPB_ERR_INVALID;
+    int64_t n = p->A->cols, m = p->A->rows;
+    double *din, *dout;
+    CHECK(host_in_out(ctx, n, m, x, &din, &dout));
+    CHECK(run_proj(ctx, p, 1, din, dout, 0, info));
+    return host_out(ctx, m, dout, v);
+}
+extern "C" int ipb_proj_row_space(ipb_ctx *ctx, ipb_proj *p, const double *b, double *y,
+                                  ipb_proj_info *info) {
+    if (!ctx || !p) return IPB_ERR_INVALID;
+    int64_t n = p->A->cols, m = p->A->rows;
+    double *din, *dout;
+    CHECK(host_in_out(ctx, m, n, b, &din, &dout));
+    CHECK(run_proj(ctx, p, 2, din, dout, 0, info));
+    return host_out(ctx, n, dout, y);
+}
+extern "C" int ipb_orthogonality(ipb_ctx *ctx, ipb_proj *p, const double *g, double *out) {
+    if (!ctx || !p || !out) return IPB_ERR_INVALID;
+    int64_t n = p->A->cols;
+    double *din, *dout;
+    CHECK(host_in_out(ctx, n, 0, g, &din, &dout));
+    ipb_proj_info info;
+    CHECK(run_proj(ctx, p, 3, din, nullptr, 0, &info));
+    *out = info.orth;
+    return IPB_OK;
+}
+
+extern "C" int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x, int iters,
+                                          double *ms) {
+    if (!ctx || !p || !x || iters <= 0 || x->len != p->A->cols) return IPB_ERR_INVALID;
+    ipb_proj_info info;
+    CHECK(run_proj(ctx, p, 4, x->d, nullptr, iters, &info));
+    if (ms) *ms = info.kernel_ms;
+    return IPB_OK;
+}
+
+// ------------------------------------------------------------------ projected CG
+static int run_pcg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, const double *dc,
+                   const double *db, double radius, const double *dlb, const double *dub,
+                   double tol, int64_t max_iter, int64_t max_inf, double *dx_out,
+                   double *d_allvecs, int64_t allvecs_cap, ipb_pcg_info *info) {
+    const int64_t n = P->A->cols, m = P->A->rows;
+    if (H->n != n) IPB_FAIL(ctx, IPB_ERR_INVALID, "H is %lld x %lld but A has %lld columns",
+                            (long long)H->n, (long long)H->n, (long long)n);
+    CHECK(ensure_ws(ctx, (size_t)7 * n));
+    PcgArgs a;
+    memset(&a, 0, sizeof a);
+    a.H = hess_view(H); a.P = proj_view(P); a.S = sync_view(ctx);
+    a.n = (int)n; a.m = (int)m;
+    a.c = dc; a.b = db; a.lb = dlb; a.ub = dub;
+    a.has_box = (dlb != nullptr && dub != nullptr);
+    a.radius = radius; a.tol = tol;
+    a.max_iter = max_iter; a.max_infeasible = max_inf;
+    double *w = ctx->ws;
+    a.x = w; a.xn = w + n; a.r = w + 2 * n; a.p = w + 3 * n; a.Hp = w + 4 * n;
+    a.xfeas = w + 5 * n; a.tmp = w + 6 * n;
+    a.allvecs = d_allvecs; a.allvecs_cap = allvecs_cap;
+    a.result = (PcgArgs::Result *)ctx->d_result;
+    float ms = 0.f;
+    int64_t work = std::max<int64_t>(n * 4, H->D ? H->nx * H->nx / 8 : 0);
+    CHECK(launch_coop(ctx, k_projected_cg, a, grid_for(ctx, work), &ms));
+    PcgArgs::Result *h = (PcgArgs::Result *)ctx->h_result;
+    CU(ctx, cudaMemcpyAsync(h, ctx->d_result, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const double *src = h->x_slot == 0 ? a.x : (h->x_slot == 1 ? a.xn : a.xfeas);
+    if (n) CU(ctx, cudaMemcpyAsync(dx_out, src, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (info) {
+        info->niter = h->niter; info->stop_cond = h->stop_cond;
+        info->hits_boundary = h->hits_boundary; info->status = h->status;
+        info->n_allvecs = h->n_allvecs; info->inner_iters = h->inner_iters;
+        info->n_solves = h->n_solves; info->n_refinements = h->n_refinements;
+        info->n_spmv_h = h->n_spmv_h; info->max_orth = h->max_orth;
+        info->tol_used = h->tol_used; info->kernel_ms = ms;
+    }
+    if (h->status == IPB_ERR_TR_INFEASIBLE)
+        IPB_FAIL(ctx, IPB_ERR_TR_INFEASIBLE, "Trust region problem does not have a solution.");
+    if (h->status == IPB_ERR_NEG_CURVATURE)
+        IPB_FAIL(ctx, IPB_ERR_NEG_CURVATURE, "Negative curvature not allowed for unrestrited problems.");
+    if (h->status != 0)
+        IPB_FAIL(ctx, h->status, "projected CG: inner solve failed (status %d)", h->status);
+    return IPB_OK;
+}
+
+extern "C" int ipb_projected_cg_dev(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P,
+                                    const ipb_vec *c, const ipb_vec *b, double trust_radius,
+                                    const ipb_vec *lb, const ipb_vec *ub, double tol,
+                                    int64_t max_iter, int64_t max_infeasible_iter,
+                                    ipb_vec *x, ipb_pcg_info *info) {
+    if (!ctx || !H || !P || !c || !b || !x) return IPB_ERR_INVALID;
+    const int64_t n = P->A->cols, m = P->A->rows;
+    if (c->len != n || b->len != m || x->len != n || (lb && lb->len != n) || (ub && ub->len != n))
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "projected_cg: vector lengths do not match A");
+    int s = run_pcg(ctx, H, P, c->d, b->d, trust_radius, lb ? lb->d : nullptr,
+                    ub ? ub->d : nullptr, tol, max_iter, max_infeasible_iter, x->d, nullptr, 0, info);
+    cudaStreamSynchronize(ctx->stream);
+    return s;
+}
+
+extern "C" int ipb_projected_cg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, const double *c,
+                                const double *b, double trust_radius, const double *lb,
+                                const double *ub, double tol, int64_t max_iter,
+                                int64_t max_infeasible_iter, double *x, double *allvecs,
+                                int64_t allvecs_cap, ipb_pcg_info *info) {
+    if (!ctx || !H || !P || !c || !b || !x) return IPB_ERR_INVALID;
+    const int64_t n = P->A->cols, m = P->A->rows;
+    const bool box = lb && ub;
+    if (!allvecs) allvecs_cap = 0;
+    size_t need = (size_t)n * (2 + (box ? 2 : 0)) + (size_t)m + (size_t)allvecs_cap * n;
+    CHECK(ensure_stage(ctx, need));
+    double *dc = ctx->stage, *db = dc + n, *dx = db + m, *dlb = dx + n, *dub = dlb + (box ? n : 0);
+    double *dall = allvecs_cap ? dub + (box ? n : 0) : nullptr;
+    if (n) CU(ctx, cudaMemcpyAsync(dc, c, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (m) CU(ctx, cudaMemcpyAsync(db, b, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (box && n) {
+        CU(ctx, cudaMemcpyAsync(dlb, lb, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(dub, ub, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ipb_pcg_info local;
+    if (!info) info = &local;
+    int s = run_pcg(ctx, H, P, dc, db, trust_radius, box ? dlb : nullptr, box ? dub : nullptr, tol,
+                    max_iter, max_infeasible_iter, dx, dall, allvecs_cap, info);
+    if (s != IPB_OK) { cudaStreamSynchronize(ctx->stream); return s; }
+    if (n) CU(ctx, cudaMemcpyAsync(x, dx, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    int64_t got = std::min<int64_t>(info->n_allvecs, allvecs_cap);
+    if (got > 0 && n)
+        CU(ctx, cudaMemcpyAsync(allvecs, dall, (size_t)got * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+// ------------------------------------------------------------------ dogleg
+extern "C" int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b, double trust_radius,
+                                   const double *lb, const double *ub, double *x,
+                                   ipb_proj_info *info) {
+    if (!ctx || !P || !b || !x) return IPB_ERR_INVALID;
+    const int64_t n = P->A->cols, m = P->A->rows;
+    const bool box = lb && ub;
+    CHECK(ensure_stage(ctx, (size_t)m + (box ? 2 * n : 0)));
+    CHECK(ensure_ws(ctx, (size_t)7 * n + m));
+    double *db = ctx->stage, *dlb = db + m, *dub = dlb + (box ? n : 0);
+    if (m) CU(ctx, cudaMemcpyAsync(db, b, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (box && n) {
+        CU(ctx, cudaMemcpyAsync(dlb, lb, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(dub, ub, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    DoglegArgs a;
+    memset(&a, 0, sizeof a);
+    a.P = proj_view(P); a.S = sync_view(ctx);
+    a.Araw = csr_view(P->A); a.Atraw = csr_view_t(P->A);
+    a.n = (int)n; a.m = (int)m; a.b = db; a.lb = box ? dlb : nullptr; a.ub = box ? dub : nullptr;
+    a.has_box = box; a.radius = trust_radius;
+    double *w = ctx->ws;
+    a.newton = w; a.cauchy = w + n; a.g = w + 2 * n; a.x1 = w + 3 * n; a.x2 = w + 4 * n;
+    a.out = w + 5 * n; a.mtmp = w + 7 * n;
+    a.result = (ProjArgs::Result *)ctx->d_result;
+    float ms = 0.f;
+    CHECK(launch_coop(ctx, k_dogleg, a, proj_grid(ctx, P), &ms));
+    ProjArgs::Result *h = (ProjArgs::Result *)ctx->h_result;
+    CU(ctx, cudaMemcpyAsync(h, ctx->d_result, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n) CU(ctx, cudaMemcpyAsync(x, a.out, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (info) {
+        info->inner_iters = h->inner_iters; info->n_solves = h->n_solves;
+        info->n_refinements = h->n_refinements; info->status = h->status;
+        info->reserved = 0; info->orth = 0.0; info->kernel_ms = ms;
+    }
+    if (h->status != 0)
+        IPB_FAIL(ctx, h->status, "modified dogleg: inner solve failed (status %d)", h->status);
+    return IPB_OK;
+}
+
+// ------------------------------------------------------------------ intersections
+extern "C" int ipb_box_sphere_intersections(ipb_ctx *ctx, int64_t n, const double *z,
+                                            const double *d, const double *lb, const double *ub,
+                                            double trust_radius, int entire_line, double *ta,
+                                            double *tb, int *intersect) {
+    if (!ctx || !z || !d || !ta || !tb || !intersect || n < 0) return IPB_ERR_INVALID;
+    const bool box = lb && ub;
+    CHECK(ensure_stage(ctx, (size_t)n * (box ? 4 : 2)));
+    double *dz = ctx->stage, *dd = dz + n, *dlb = dd + n, *dub = dlb + (box ? n : 0);
+    if (n) {
+        CU(ctx, cudaMemcpyAsync(dz, z, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(dd, d, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (box) {
+            CU(ctx, cudaMemcpyAsync(dlb, lb, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(dub, ub, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    IntersectArgs a;
+    memset(&a, 0, sizeof a);
+    a.S = sync_view(ctx); a.n = (int)n; a.z = dz; a.d = dd;
+    a.lb = box ? dlb : nullptr; a.ub = box ? dub : nullptr;
+    a.has_box = box; a.line = entire_line; a.radius = trust_radius;
+    a.result = (IntersectArgs::Result *)ctx->d_result;
+    CHECK(launch_coop(ctx, k_intersect, a, grid_for(ctx, n), nullptr));
+    IntersectArgs::Result *h = (IntersectArgs::Result *)ctx->h_result;
+    CU(ctx, cudaMemcpyAsync(h, ctx->d_result, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *ta = h->ta; *tb = h->tb; *intersect = h->hit;
+    return IPB_OK;
+}

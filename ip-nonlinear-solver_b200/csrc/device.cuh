@@ -1,0 +1,1090 @@
+// Device side of the B200-native projected-CG / null-space-projection path.
+//
+// Design:
+//   * every operation of the path -- a projector application, a whole
+//     projected-CG solve, a dogleg step -- is ONE persistent cooperative
+//     kernel: the grid is sized to what is co-resident on the 148 SMs, phases
+//     are grid-stride loops separated by a grid barrier, and every scalar the
+//     control flow needs (alpha, beta, norms, intersection parameters,
+//     convergence flags) is reduced on the device in a fixed order and read
+//     by every CTA, so all CTAs take identical branches and nothing but a
+//     small result struct returns to the host;
+//   * SpMV is CSR-stream: a CTA stages the products val*x[col] of a
+//     contiguous nnz range in shared memory with fully coalesced loads, then
+//     each thread sums its rows from shared memory in index order (the same
+//     left-to-right order as scipy's csr_matvec, so with -fmad=false row
+//     sums are bit-identical to the reference's);
+//   * (A A')^-1 is a single-reduction (Chronopoulos-Gear) CG on the
+//     row-normalised A: one SpMV with A', one with A (dot products fused in
+//     its epilogue) and one fused 4-vector update per iteration.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace ipb {
+
+constexpr int THREADS = 256;          // threads per CTA of every kernel
+constexpr int WARPS = THREADS / 32;
+constexpr int CHUNK = 3072;           // products staged per pass (24 KB smem)
+constexpr int RPT_MAX = 8;            // max rows per thread in one row block
+constexpr int NSLOT = 8;              // reduction slots per barrier
+constexpr int MAX_GRID = 2048;        // upper bound on CTAs of a launch
+
+enum { OP_SUM = 0, OP_MIN = 1, OP_MAX = 2 };
+
+// ---------------------------------------------------------------- structs
+struct CsrView {
+    int rows, cols;
+    int rpt;                  // rows per thread: a row block is rpt*THREADS rows
+    const int *rowptr;
+    const int *col;
+    const double *val;
+};
+
+struct HessView {
+    int n, nx;                // H = blockdiag(S + D (nx x nx), diag(tail))
+    int has_csr, has_dense, has_tail;
+    CsrView S;
+    const double *D;          // row-major nx x nx
+    const double *tail;       // n - nx
+};
+
+struct SyncView {
+    unsigned *barrier;        // sense-reversing arrival counter
+    double *partials;         // [NSLOT][MAX_GRID]
+    int *abort_flag;          // set when a spin times out
+};
+
+struct ProjView {
+    int m, n;
+    CsrView A;                // row-normalised A  (At = its transpose)
+    CsrView At;
+    const double *dscale;     // 1/||a_i|| (0 for empty rows)
+    const double *dnorm2;     // ||a_i||^2
+    double fro;               // ||A||_F of the un-normalised A
+    double orth_tol;
+    int max_refin;
+    double rtol;
+    int maxit;
+    // work vectors
+    double *v, *r, *w, *p, *s, *rhs;   // m
+    double *t;                          // n
+};
+
+struct ProjStats {
+    long long inner_iters, n_solves, n_refinements;
+    int status;
+    double orth, max_orth;
+};
+
+// ---------------------------------------------------------------- loads
+__device__ __forceinline__ double ldg_stream(const double *p) {
+    return __ldg(p);
+}
+__device__ __forceinline__ int ldg_stream(const int *p) { return __ldg(p); }
+
+// ---------------------------------------------------------------- barrier
+// Same protocol as cooperative_groups::grid_group::sync (release add by the
+// CTA master, acquire poll), written out so the reduction and -- later -- the
+// cross-GPU exchange can ride on it.  Requires all CTAs co-resident
+// (cudaLaunchCooperativeKernel).
+__device__ __forceinline__ void grid_sync(const SyncView &S) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned nb = 1;
+        if (blockIdx.x == 0) nb = 0x80000000u - (gridDim.x - 1);
+        unsigned old, cur;
+        asm volatile("atom.add.release.gpu.u32 %0,[%1],%2;"
+                     : "=r"(old) : "l"(S.barrier), "r"(nb) : "memory");
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0,[%1];"
+                         : "=r"(cur) : "l"(S.barrier) : "memory");
+            if (++spins > (1ll << 31)) { *S.abort_flag = 1; __trap(); }
+        } while (((old ^ cur) & 0x80000000u) == 0);
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ double comb(double a, double b, int op) {
+    if (op == OP_SUM) return a + b;
+    if (op == OP_MIN) return fmin(a, b);
+    return fmax(a, b);
+}
+__device__ __forceinline__ double ident(int op) {
+    if (op == OP_SUM) return 0.0;
+    if (op == OP_MIN) return INFINITY;
+    return -INFINITY;
+}
+
+__device__ __forceinline__ double warp_reduce(double v, int op) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = comb(v, __shfl_xor_sync(0xffffffffu, v, o), op);
+    return v;
+}
+
+// Block-reduce ``v`` and publish it as this CTA's partial of ``slot``.
+// red: shared scratch of WARPS doubles.  Fixed tree => deterministic.
+__device__ __forceinline__ void publish(const SyncView &S, int slot, double v,
+                                        int op, double *red) {
+    v = warp_reduce(v, op);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = red[0];
+#pragma unroll
+        for (int w = 1; w < WARPS; ++w) a = comb(a, red[w], op);
+        S.partials[slot * MAX_GRID + blockIdx.x] = a;
+    }
+}
+
+// After a grid_sync: every CTA combines all CTAs' partials of slots
+// [0, nslots) in the same fixed order, so every thread of the grid sees
+// bit-identical values.  out: shared array of NSLOT doubles.
+__device__ __forceinline__ void collect(const SyncView &S, int nslots,
+                                        const int *ops, double *out) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int slot = warp; slot < nslots; slot += WARPS) {
+        int op = ops[slot];
+        double a = ident(op);
+        for (int i = lane; i < (int)gridDim.x; i += 32)
+            a = comb(a, __ldcg(&S.partials[slot * MAX_GRID + i]), op);
+        a = warp_reduce(a, op);
+        if (lane == 0) out[slot] = a;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- SpMV
+// Row epilogue: y_r = sa*s + sb*addv[r] (+ y_r when accumulate); optional
+// running sums  acc0 += y_r*dotv[r],  acc1 += y_r^2 * (wv ? wv[r] : 1).
+struct Epi {
+    double *y;
+    const double *addv;
+    double sa, sb;
+    const double *dotv;
+    const double *wv;
+    int want_sq;
+    int accumulate;
+};
+
+__device__ __forceinline__ Epi epi_plain(double *y) {
+    Epi e; e.y = y; e.addv = nullptr; e.sa = 1.0; e.sb = 0.0; e.dotv = nullptr;
+    e.wv = nullptr; e.want_sq = 0; e.accumulate = 0; return e;
+}
+
+__device__ __forceinline__ void row_out(const Epi &e, int r, double s,
+                                        double &acc0, double &acc1) {
+    double y = s;
+    if (e.sa != 1.0) y = e.sa * y;
+    if (e.addv) y = y + e.sb * e.addv[r];
+    if (e.accumulate) y = e.y[r] + y;
+    e.y[r] = y;
+    if (e.dotv) acc0 += y * e.dotv[r];
+    if (e.want_sq) acc1 += (e.wv ? e.wv[r] * (y * y) : y * y);
+}
+
+// y = M x over all row blocks of M (grid-stride).  prod: CHUNK doubles smem.
+__device__ __noinline__ void spmv(const CsrView M, const double *x, const Epi e,
+                                  double *prod, double &acc0, double &acc1) {
+    const int R = M.rpt * THREADS;
+    const int nblk = (M.rows + R - 1) / R;
+    const int tid = threadIdx.x;
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int r0 = blk * R;
+        const int r1 = min(r0 + R, M.rows);
+        const int p0 = ldg_stream(M.rowptr + r0);
+        const int p1 = ldg_stream(M.rowptr + r1);
+        int rs[RPT_MAX], re[RPT_MAX];
+        double acc[RPT_MAX];
+#pragma unroll
+        for (int j = 0; j < RPT_MAX; ++j) {
+            int r = r0 + tid + j * THREADS;
+            acc[j] = 0.0;
+            if (j < M.rpt && r < r1) {
+                rs[j] = ldg_stream(M.rowptr + r);
+                re[j] = ldg_stream(M.rowptr + r + 1);
+            } else {
+                rs[j] = re[j] = p1;
+            }
+        }
+        for (int p = p0; p < p1; p += CHUNK) {
+            const int len = min(CHUNK, p1 - p);
+            // stage products, coalesced over the nnz range
+#pragma unroll 4
+            for (int k = tid; k < len; k += THREADS) {
+                double a = ldg_stream(M.val + p + k);
+                int c = ldg_stream(M.col + p + k);
+                prod[k] = a * x[c];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < RPT_MAX; ++j) {
+                if (j < M.rpt) {
+                    int a = max(rs[j], p) - p, b = min(re[j], p + len) - p;
+                    double s = acc[j];
+                    for (int k = a; k < b; ++k) s += prod[k];
+                    acc[j] = s;
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < RPT_MAX; ++j) {
+            int r = r0 + tid + j * THREADS;
+            if (j < M.rpt && r < r1) row_out(e, r, acc[j], acc0, acc1);
+        }
+    }
+}
+
+// Dense row-major GEMV, one warp per row, same epilogue.
+__device__ __noinline__ void gemv_dense(const double *D, int nx, const double *x,
+                                        const Epi e, double &acc0, double &acc1) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    const int nw = gridDim.x * WARPS;
+    for (int r = gw; r < nx; r += nw) {
+        const double *row = D + (size_t)r * nx;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int c = lane;
+        for (; c + 96 < nx; c += 128) {
+            s0 += ldg_stream(row + c) * x[c];
+            s1 += ldg_stream(row + c + 32) * x[c + 32];
+            s2 += ldg_stream(row + c + 64) * x[c + 64];
+            s3 += ldg_stream(row + c + 96) * x[c + 96];
+        }
+        for (; c < nx; c += 32) s0 += ldg_stream(row + c) * x[c];
+        double s = warp_reduce((s0 + s1) + (s2 + s3), OP_SUM);
+        if (lane == 0) row_out(e, r, s, acc0, acc1);
+    }
+}
+
+// y = H x  with optional  acc0 += y.dotv.  Phases that accumulate into y are
+// separated by a grid barrier because row->CTA maps differ between terms.
+__device__ __noinline__ void hess_apply(const HessView &H, const SyncView &S,
+                                        const double *x, double *y,
+                                        const double *dotv, double *prod,
+                                        double &acc0) {
+    double dummy = 0.0;
+    Epi e = epi_plain(y);
+    if (H.has_dense) {
+        Epi ed = e;
+        if (!H.has_csr) ed.dotv = dotv;
+        gemv_dense(H.D, H.nx, x, ed, acc0, dummy);
+        if (H.has_csr) grid_sync(S);
+    }
+    if (H.has_csr) {
+        Epi es = e;
+        es.accumulate = H.has_dense;
+        es.dotv = dotv;
+        spmv(H.S, x, es, prod, acc0, dummy);
+    }
+    const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+    if (!H.has_dense && !H.has_csr) {
+        for (int i = gt; i < H.nx; i += nt) y[i] = 0.0;
+    }
+    if (H.has_tail) {
+        for (int i = H.nx + gt; i < H.n; i += nt) {
+            double v = H.tail[i - H.nx] * x[i];
+            y[i] = v;
+            if (dotv) acc0 += v * dotv[i];
+        }
+    } else {
+        for (int i = H.nx + gt; i < H.n; i += nt) y[i] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------- shared memory
+struct Smem {
+    double prod[CHUNK];
+    double red[WARPS];
+    double out[NSLOT];
+    int ops[NSLOT];
+};
+
+__device__ __forceinline__ void set_ops(Smem &sm, int o0, int o1 = 0, int o2 = 0,
+                                        int o3 = 0, int o4 = 0, int o5 = 0,
+                                        int o6 = 0, int o7 = 0) {
+    if (threadIdx.x == 0) {
+        sm.ops[0] = o0; sm.ops[1] = o1; sm.ops[2] = o2; sm.ops[3] = o3;
+        sm.ops[4] = o4; sm.ops[5] = o5; sm.ops[6] = o6; sm.ops[7] = o7;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- inner CG
+// Solve (A~ A~') v = rhs, A~ the row-normalised A, rhs in P.rhs, v in P.v.
+// Chronopoulos-Gear single-reduction CG:
+//   r = rhs; w = M r; gamma = r.r; delta = r.w; alpha = gamma/delta; beta = 0
+//   loop:  p = r + beta p;  s = w + beta s;  v += alpha p;  r -= alpha s
+//          w = M r; gamma' = r.r; delta' = r.w           (one reduction)
+//          beta = gamma'/gamma; alpha = gamma'/(delta' - beta*gamma'/alpha)
+// Every CTA returns the same iteration count.  fixed_iters > 0 runs exactly
+// that many iterations without a convergence test (bench only).
+__device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
+                                        Smem &sm, ProjStats &st,
+                                        int fixed_iters = 0) {
+    const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+    const int m = P.m;
+    double a0, a1;
+    // r = rhs, v = p = s = 0
+    double gpart = 0.0;
+    for (int i = gt; i < m; i += nt) {
+        double ri = P.rhs[i];
+        P.r[i] = ri; P.v[i] = 0.0; P.p[i] = 0.0; P.s[i] = 0.0;
+        gpart += ri * ri;
+    }
+    grid_sync(S);
+    a0 = a1 = 0.0;
+    spmv(P.At, P.r, epi_plain(P.t), sm.prod, a0, a1);
+    grid_sync(S);
+    {
+        Epi e = epi_plain(P.w);
+        e.dotv = P.r;
+        a0 = 0.0; a1 = 0.0;
+        spmv(P.A, P.t, e, sm.prod, a0, a1);
+        publish(S, 0, a0, OP_SUM, sm.red);
+        publish(S, 1, gpart, OP_SUM, sm.red);
+    }
+    set_ops(sm, OP_SUM, OP_SUM);
+    grid_sync(S);
+    collect(S, 2, sm.ops, sm.out);
+    double delta = sm.out[0], gamma = sm.out[1];
+    const double gamma0 = gamma;
+    st.n_solves += 1;
+    if (!(gamma0 > 0.0)) return 0;           // zero right-hand side: v = 0
+    if (!(delta > 0.0)) { st.status = 5; return 0; }
+    double alpha = gamma / delta, beta = 0.0;
+    const double target = P.rtol * P.rtol * gamma0;
+    const int maxit = fixed_iters > 0 ? fixed_iters : P.maxit;
+    int k = 0;
+    while (k < maxit) {
+        ++k;
+        gpart = 0.0;
+        for (int i = gt; i < m; i += nt) {
+            double ri = P.r[i], wi = P.w[i];
+            double pi = ri + beta * P.p[i];
+            double si = wi + beta * P.s[i];
+            P.p[i] = pi; P.s[i] = si;
+            P.v[i] = P.v[i] + alpha * pi;
+            ri = ri - alpha * si;
+            P.r[i] = ri;
+            gpart += ri * ri;
+        }
+        grid_sync(S);
+        a0 = a1 = 0.0;
+        spmv(P.At, P.r, epi_plain(P.t), sm.prod, a0, a1);
+        grid_sync(S);
+        {
+            Epi e = epi_plain(P.w);
+            e.dotv = P.r;
+            a0 = 0.0; a1 = 0.0;
+            spmv(P.A, P.t, e, sm.prod, a0, a1);
+            double g = 0.0;
+            for (int i = gt; i < m; i += nt) { double ri = P.r[i]; g += ri * ri; }
+            publish(S, 0, a0, OP_SUM, sm.red);
+            publish(S, 1, g, OP_SUM, sm.red);
+        }
+        grid_sync(S);
+        collect(S, 2, sm.ops, sm.out);
+        double delta2 = sm.out[0], gamma2 = sm.out[1];
+        if (fixed_iters <= 0 && gamma2 <= target) break;
+        beta = gamma2 / gamma;
+        double denom = delta2 - beta * gamma2 / alpha;
+        if (!(denom > 0.0) || !(gamma2 == gamma2)) {
+            if (fixed_iters <= 0) { st.status = 5; break; }
+            denom = delta2;   // keep the bench loop finite
+        }
+        alpha = gamma2 / denom;
+        gamma = gamma2;
+    }
+    st.inner_iters += k;
+    if (fixed_iters <= 0 && k >= maxit && st.status == 0) {
+        // not converged to rtol: leave it to the refinement loop / caller
+    }
+    return k;
+}
+
+// z = x - A~'(A~A~')^-1 A~ x, then iterative refinement while
+// orthogonality(A, z) > orth_tol (projections.py:65-80).  x and z may alias.
+// Returns ||z||^2 (identical in every thread).
+__device__ __noinline__ double null_space(const ProjView &P, const SyncView &S,
+                                          Smem &sm, ProjStats &st,
+                                          const double *x, double *z) {
+    const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+    double a0, a1;
+    if (P.m == 0) {                                  // Z = I
+        double zz = 0.0;
+        for (int i = gt; i < P.n; i += nt) { double v = x[i]; z[i] = v; zz += v * v; }
+        publish(S, 0, zz, OP_SUM, sm.red);
+        set_ops(sm, OP_SUM);
+        grid_sync(S);
+        collect(S, 1, sm.ops, sm.out);
+        st.orth = 0.0;
+        return sm.out[0];
+    }
+    a0 = a1 = 0.0;
+    spmv(P.A, x, epi_plain(P.rhs), sm.prod, a0, a1);
+    grid_sync(S);
+    inner_solve(P, S, sm, st);
+    const double *src = x;
+    double zz = 0.0;
+    int k = 0;
+    while (true) {
+        // z = src - A~' v, ||z||^2
+        {
+            Epi e = epi_plain(z);
+            e.sa = -1.0; e.addv = src; e.sb = 1.0; e.want_sq = 1;
+            a0 = a1 = 0.0;
+            spmv(P.At, P.v, e, sm.prod, a0, a1);
+            publish(S, 0, a1, OP_SUM, sm.red);
+        }
+        grid_sync(S);
+        // w~ = A~ z (next right-hand side), ||A z||^2 = sum d_i w~_i^2
+        {
+            Epi e = epi_plain(P.rhs);
+            e.want_sq = 1; e.wv = P.dnorm2;
+            a0 = a1 = 0.0;
+            spmv(P.A, z, e, sm.prod, a0, a1);
+            publish(S, 1, a1, OP_SUM, sm.red);
+        }
+        set_ops(sm, OP_SUM, OP_SUM);
+        grid_sync(S);
+        collect(S, 2, sm.ops, sm.out);
+        zz = sm.out[0];
+        double az = sm.out[1];
+        double orth = 0.0;
+        double ng = sqrt(zz);
+        if (ng != 0.0 && P.fro != 0.0) orth = sqrt(az) / (P.fro * ng);
+        st.orth = orth;
+        if (!(orth > P.orth_tol) || k >= P.max_refin) break;
+        // refine: solve M dv = A~ z, z -= A~' dv
+        inner_solve(P, S, sm, st);
+        st.n_refinements += 1;
+        src = z;
+        ++k;
+    }
+    if (st.orth > st.max_orth) st.max_orth = st.orth;
+    return zz;
+}
+
+// v_out = (A A')^-1 A x = D^-1/2 (A~A~')^-1 A~ x
+__device__ __noinline__ void least_squares(const ProjView &P, const SyncView &S,
+                                           Smem &sm, ProjStats &st,
+                                           const double *x, double *vout) {
+    const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+    if (P.m == 0) return;
+    double a0 = 0.0, a1 = 0.0;
+    spmv(P.A, x, epi_plain(P.rhs), sm.prod, a0, a1);
+    grid_sync(S);
+    inner_solve(P, S, sm, st);
+    for (int i = gt; i < P.m; i += nt) vout[i] = P.dscale[i] * P.v[i];
+}
+
+// y = A'(A A')^-1 (sign*b) = A~' (A~A~')^-1 D^-1/2 (sign*b); returns via
+// slot 0 the squared norm of y when want_norm.
+__device__ __noinline__ double row_space(const ProjView &P, const SyncView &S,
+                                         Smem &sm, ProjStats &st,
+                                         const double *b, double sign, double *y) {
+    const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+    if (P.m == 0) {
+        for (int i = gt; i < P.n; i += nt) y[i] = 0.0;
+        return 0.0;
+    }
+    for (int i = gt; i < P.m; i += nt) P.rhs[i] = P.dscale[i] * (sign * b[i]);
+    grid_sync(S);
+    inner_solve(P, S, sm, st);
+    Epi e = epi_plain(y);
+    e.want_sq = 1;
+    double a0 = 0.0, a1 = 0.0;
+    spmv(P.At, P.v, e, sm.prod, a0, a1);
+    publish(S, 0, a1, OP_SUM, sm.red);
+    set_ops(sm, OP_SUM);
+    grid_sync(S);
+    collect(S, 1, sm.ops, sm.out);
+    return sm.out[0];
+}
+
+// ---------------------------------------------------------------- intersections
+struct Interval { double ta, tb; int hit; };
+
+// sphere_intersections (qp_subproblem.py:66-149) from the three dot products.
+__device__ __forceinline__ Interval ball_interval(double dd, double zd, double zz,
+                                                  double radius, int line) {
+    Interval I;
+    if (dd == 0.0) { I.ta = 0; I.tb = 0; I.hit = 0; return I; }   // norm(d) == 0
+    if (isinf(radius)) {
+        I.hit = 1;
+        if (line) { I.ta = -INFINITY; I.tb = INFINITY; } else { I.ta = 0; I.tb = 1; }
+        return I;
+    }
+    double a = dd, b = 2 * zd, c = zz - radius * radius;
+    double disc = b * b - 4 * a * c;
+    if (disc < 0) { I.ta = 0; I.tb = 0; I.hit = 0; return I; }
+    double sq = sqrt(disc);
+    double aux = b + copysign(sq, b);
+    double ta = -aux / (2 * a), tb = -2 * c / aux;
+    if (tb < ta) { double t = ta; ta = tb; tb = t; }
+    if (line) { I.ta = ta; I.tb = tb; I.hit = 1; return I; }
+    if (tb < 0 || ta > 1) { I.ta = 0; I.tb = 0; I.hit = 0; return I; }
+    I.ta = fmax(0.0, ta); I.tb = fmin(1.0, tb); I.hit = 1;
+    return I;
+}
+
+// box_intersections (:152-234) from the reduced extrema.
+__device__ __forceinline__ Interval box_interval(double dd, double tlo, double thi,
+                                                 double bad_fixed, int line) {
+    Interval I;
+    if (dd == 0.0 || bad_fixed > 0.0) { I.ta = 0; I.tb = 0; I.hit = 0; return I; }
+    I.hit = (tlo <= thi);
+    if (!line) {
+        if (thi < 0 || tlo > 1) { I.ta = 0; I.tb = 0; I.hit = 0; return I; }
+        tlo = fmax(0.0, tlo); thi = fmin(1.0, thi);
+    }
+    I.ta = tlo; I.tb = thi;
+    return I;
+}
+
+// box_sphere_intersections(z, scale*dvec, lb, ub, radius, line) (:237-303).
+// One fused pass over z, dvec (and lb, ub when has_box); one barrier.
+__device__ __noinline__ Interval box_ball(const SyncView &S, Smem &sm, int n,
+                                          const double *z, const double *dvec,
+                                          double scale, const double *lb,
+                                          const double *ub, int has_box,
+                                          double radius, int line) {
+    const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+    double dd = 0, zd = 0, zz = 0, tlo = -INFINITY, thi = INFINITY, bad = 0;
+    for (int i = gt; i < n; i += nt) {
+        double zi = z[i], di = scale * dvec[i];
+        dd += di * di; zd += zi * di; zz += zi * zi;
+        if (has_box) {
+            double l = lb[i], u = ub[i];
+            if (di == 0.0) {
+                if (zi < l || zi > u) bad = 1.0;
+            } else {
+                double t1 = (l - zi) / di, t2 = (u - zi) / di;
+                tlo = fmax(tlo, fmin(t1, t2));
+                thi = fmin(thi, fmax(t1, t2));
+            }
+        }
+    }
+    publish(S, 0, dd, OP_SUM, sm.red);
+    publish(S, 1, zd, OP_SUM, sm.red);
+    publish(S, 2, zz, OP_SUM, sm.red);
+    publish(S, 3, tlo, OP_MAX, sm.red);
+    publish(S, 4, thi, OP_MIN, sm.red);
+    publish(S, 5, bad, OP_MAX, sm.red);
+    set_ops(sm, OP_SUM, OP_SUM, OP_SUM, OP_MAX, OP_MIN, OP_MAX);
+    grid_sync(S);
+    collect(S, 6, sm.ops, sm.out);
+    dd = sm.out[0]; zd = sm.out[1]; zz = sm.out[2];
+    // norm(d) == 0 test of the reference is on sqrt(dd)
+    Interval Ib;
+    if (has_box) Ib = box_interval(dd, sm.out[3], sm.out[4], sm.out[5], line);
+    else {
+        // unbounded box: every t is feasible unless d == 0
+        if (dd == 0.0) { Ib.ta = 0; Ib.tb = 0; Ib.hit = 0; }
+        else if (line) { Ib.ta = -INFINITY; Ib.tb = INFINITY; Ib.hit = 1; }
+        else { Ib.ta = 0; Ib.tb = 1; Ib.hit = 1; }
+    }
+    Interval Is = ball_interval(dd, zd, zz, radius, line);
+    Interval I;
+    I.ta = fmax(Ib.ta, Is.ta);
+    I.tb = fmin(Ib.tb, Is.tb);
+    I.hit = (Ib.hit && Is.hit && I.ta <= I.tb);
+    __syncthreads();
+    return I;
+}
+
+__device__ __forceinline__ double clipd(double x, double l, double u) {
+    return fmin(fmax(x, l), u);
+}
+
+// ---------------------------------------------------------------- projected CG
+struct PcgArgs {
+    HessView H;
+    ProjView P;
+    SyncView S;
+    int n, m;
+    const double *c, *b, *lb, *ub;     // lb/ub null when has_box == 0
+    int has_box;
+    double radius, tol;                // tol < 0 or NaN: default rule
+    long long max_iter, max_infeasible;
+    // work vectors (n): x, xn, r, p, Hp, xfeas, tmp
+    double *x, *xn, *r, *p, *Hp, *xfeas, *tmp;
+    double *allvecs; long long allvecs_cap;
+    // result
+    struct Result {
+        long long niter;
+        int stop_cond, hits_boundary, status, n_allvecs;
+        long long inner_iters, n_solves, n_refinements, n_spmv_h;
+        double max_orth, tol_used;
+        int x_slot;                    // 0: result in x, 1: xn, 2: xfeas
+    } *result;
+};
+
+__device__ __forceinline__ void store_allvec(const PcgArgs &a, int &count,
+                                             const double *v) {
+    if (!a.allvecs) return;
+    if (count < a.allvecs_cap) {
+        const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+        double *dst = a.allvecs + (size_t)count * a.n;
+        for (int i = gt; i < a.n; i += nt) dst[i] = v[i];
+    }
+    ++count;
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_projected_cg(const PcgArgs a) {
+    __shared__ Smem sm;
+    const SyncView &S = a.S;
+    const int n = a.n;
+    const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+    ProjStats st = {0, 0, 0, 0, 0.0, 0.0};
+    double *x = a.x, *xn = a.xn, *r = a.r, *p = a.p, *Hp = a.Hp;
+    long long n_spmv_h = 0;
+    int nvec = 0;
+    int status = 0, stop_cond = 1, hits = 0;
+    long long k = 0;
+    double tol = a.tol;
+    double acc0, acc1;
+    int x_slot = 0;
+
+    // ---- x = Y(-b)  (:502); exactly 0 when b == 0, as in the reference
+    double bb = 0.0;
+    for (int i = gt; i < a.m; i += nt) { double v = a.b[i]; bb += v * v; }
+    publish(S, 0, bb, OP_SUM, sm.red);
+    set_ops(sm, OP_SUM);
+    grid_sync(S);
+    collect(S, 1, sm.ops, sm.out);
+    bb = sm.out[0];
+    double xx = 0.0;
+    if (bb > 0.0) {
+        xx = row_space(a.P, S, sm, st, a.b, -1.0, x);
+    } else {
+        for (int i = gt; i < n; i += nt) x[i] = 0.0;
+        grid_sync(S);
+    }
+    // ---- r = Z(H x + c), g = Z r, p = -g  (:503-505)
+    if (bb > 0.0) {
+        acc0 = 0.0;
+        hess_apply(a.H, S, x, a.tmp, nullptr, sm.prod, acc0);
+        ++n_spmv_h;
+        grid_sync(S);
+        for (int i = gt; i < n; i += nt) a.tmp[i] = a.tmp[i] + a.c[i];
+    } else {
+        for (int i = gt; i < n; i += nt) a.tmp[i] = 0.0 + a.c[i];
+    }
+    grid_sync(S);
+    null_space(a.P, S, sm, st, a.tmp, r);
+    grid_sync(S);
+    double gg = null_space(a.P, S, sm, st, r, r);      // r now holds g
+    for (int i = gt; i < n; i += nt) p[i] = -r[i];
+    grid_sync(S);
+    store_allvec(a, nvec, x);
+    // ---- H_p = H p, rt_g = ||g||^2  (:511-512)
+    acc0 = 0.0;
+    hess_apply(a.H, S, p, Hp, p, sm.prod, acc0);
+    ++n_spmv_h;
+    publish(S, 0, acc0, OP_SUM, sm.red);
+    set_ops(sm, OP_SUM);
+    grid_sync(S);
+    collect(S, 1, sm.ops, sm.out);
+    double pHp = sm.out[0];
+    double ng = sqrt(gg);
+    double rt_g = ng * ng;
+
+    // ---- trust-region feasibility of x  (:515-526)
+    double tr_distance = a.radius - sqrt(xx);
+    bool done = false;
+    if (tr_distance < 0) { status = 3; done = true; }
+    else if (tr_distance < 1e-25) {
+        stop_cond = 2; hits = 1; done = true;
+        store_allvec(a, nvec, x);
+    }
+    if (!(tol >= 0.0))                                   // default (:529-530)
+        tol = fmax(fmin(0.01 * sqrt(rt_g), 0.1 * rt_g), 1e-25);
+    long long nm = (long long)n - a.m;
+    long long max_iter = a.max_iter < 0 ? nm : a.max_iter;
+    if (max_iter > nm) max_iter = nm;
+    long long max_inf = a.max_infeasible < 0 ? nm : a.max_infeasible;
+    long long counter = 0;
+    bool have_feas = false;
+
+    if (!done) {
+        // last_feasible_x: zeros (the reference leaves it uninitialised, :547)
+        if (a.has_box) for (int i = gt; i < n; i += nt) a.xfeas[i] = 0.0;
+        for (long long it = 0; it < max_iter; ++it) {
+            if (rt_g < tol) { stop_cond = 4; break; }              // :551-553
+            ++k;
+            if (pHp <= 0) {                                          // :558-576
+                if (isinf(a.radius)) { status = 4; break; }
+                Interval I = box_ball(S, sm, n, x, p, 1.0, a.lb, a.ub, a.has_box,
+                                      a.radius, 1);
+                double alpha = I.tb;
+                for (int i = gt; i < n; i += nt) {
+                    double v = x[i];
+                    if (I.hit) v = v + alpha * p[i];
+                    if (a.has_box) v = clipd(v, a.lb[i], a.ub[i]);
+                    x[i] = v;
+                }
+                stop_cond = 3; hits = 1;
+                break;
+            }
+            double alpha = rt_g / pHp;                               // :579-580
+            // x_next = x + alpha p; ||x_next||^2; inside-box flag;
+            // r_next = r + alpha H_p (:622) in the same pass.
+            double sq = 0.0, out = 0.0;
+            for (int i = gt; i < n; i += nt) {
+                double pi = p[i];
+                double v = x[i] + alpha * pi;
+                xn[i] = v;
+                sq += v * v;
+                if (a.has_box && (v < a.lb[i] || v > a.ub[i])) out = 1.0;
+                a.tmp[i] = r[i] + alpha * Hp[i];
+            }
+            publish(S, 0, sq, OP_SUM, sm.red);
+            publish(S, 1, out, OP_MAX, sm.red);
+            set_ops(sm, OP_SUM, OP_MAX);
+            grid_sync(S);
+            collect(S, 2, sm.ops, sm.out);
+            double nxn = sqrt(sm.out[0]);
+            bool inside = !(sm.out[1] > 0.0);
+            if (nxn >= a.radius) {                                   // :583-596
+                Interval I = box_ball(S, sm, n, x, p, alpha, a.lb, a.ub, a.has_box,
+                                      a.radius, 0);
+                double ta = I.tb * alpha;                            // theta*alpha
+                for (int i = gt; i < n; i += nt) {
+                    double v = x[i];
+                    if (I.hit) v = v + ta * p[i];
+                    if (a.has_box) v = clipd(v, a.lb[i], a.ub[i]);
+                    x[i] = v;
+                }
+                stop_cond = 2; hits = 1;
+                break;
+            }
+            if (inside) counter = 0; else ++counter;                 // :599-613
+            if (counter > 0) {
+                Interval I = box_ball(S, sm, n, x, p, alpha, a.lb, a.ub, a.has_box,
+                                      a.radius, 0);
+                if (I.hit) {
+                    double ta = I.tb * alpha;
+                    for (int i = gt; i < n; i += nt)
+                        a.xfeas[i] = clipd(x[i] + ta * p[i], a.lb[i], a.ub[i]);
+                    counter = 0;
+                    have_feas = true;
+                }
+            }
+            if (counter > max_inf) break;                            // :615-616
+            store_allvec(a, nvec, xn);
+            // g_next = Z r_next (:624);  r <- g_next (:632)
+            double gg2 = null_space(a.P, S, sm, st, a.tmp, r);
+            double ng2 = sqrt(gg2);
+            double rt_g_next = ng2 * ng2;                            // :626
+            double beta = rt_g_next / rt_g;                          // :627
+            for (int i = gt; i < n; i += nt) p[i] = -r[i] + beta * p[i];   // :628
+            { double *t = x; x = xn; xn = t; x_slot ^= 1; }          // :630
+            rt_g = rt_g_next;                                        // :633
+            grid_sync(S);
+            acc0 = 0.0;                                              // :634
+            hess_apply(a.H, S, p, Hp, p, sm.prod, acc0);
+            ++n_spmv_h;
+            publish(S, 0, acc0, OP_SUM, sm.red);
+            set_ops(sm, OP_SUM);
+            grid_sync(S);
+            collect(S, 1, sm.ops, sm.out);
+            pHp = sm.out[0];
+        }
+    }
+    // ---- final feasibility fix-up (:636-638)
+    int final_slot = x_slot;
+    if (status == 0 && a.has_box) {
+        grid_sync(S);
+        double out = 0.0;
+        for (int i = gt; i < n; i += nt) {
+            double v = x[i];
+            if (v < a.lb[i] || v > a.ub[i]) out = 1.0;
+        }
+        publish(S, 0, out, OP_MAX, sm.red);
+        set_ops(sm, OP_MAX);
+        grid_sync(S);
+        collect(S, 1, sm.ops, sm.out);
+        if (sm.out[0] > 0.0) { final_slot = 2; hits = 1; }
+    }
+    (void)have_feas;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        PcgArgs::Result &R = *a.result;
+        R.niter = k; R.stop_cond = stop_cond; R.hits_boundary = hits;
+        R.status = status ? status : st.status;
+        R.n_allvecs = nvec;
+        R.inner_iters = st.inner_iters; R.n_solves = st.n_solves;
+        R.n_refinements = st.n_refinements; R.n_spmv_h = n_spmv_h;
+        R.max_orth = st.max_orth; R.tol_used = tol;
+        R.x_slot = final_slot;
+    }
+}
+
+// ---------------------------------------------------------------- projector kernels
+struct ProjArgs {
+    ProjView P;
+    SyncView S;
+    int op;                      // 0: Z, 1: LS, 2: Y, 3: orthogonality, 4: bench
+    const double *in;
+    double *out;
+    int fixed_iters;
+    struct Result {
+        long long inner_iters, n_solves, n_refinements;
+        int status;
+        double orth;
+    } *result;
+};
+
+__global__ void __launch_bounds__(THREADS)
+k_projector(const ProjArgs a) {
+    __shared__ Smem sm;
+    ProjStats st = {0, 0, 0, 0, 0.0, 0.0};
+    const SyncView &S = a.S;
+    const ProjView &P = a.P;
+    if (a.op == 0) {
+        null_space(P, S, sm, st, a.in, a.out);
+    } else if (a.op == 1) {
+        least_squares(P, S, sm, st, a.in, a.out);
+    } else if (a.op == 2) {
+        row_space(P, S, sm, st, a.in, 1.0, a.out);
+    } else if (a.op == 3) {
+        // orthogonality(A, g): ||A g|| / (||A||_F ||g||)
+        const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+        double gg = 0.0, a0 = 0.0, a1 = 0.0;
+        for (int i = gt; i < P.n; i += nt) { double v = a.in[i]; gg += v * v; }
+        if (P.m > 0) {
+            Epi e = epi_plain(P.rhs);
+            e.want_sq = 1; e.wv = P.dnorm2;
+            spmv(P.A, a.in, e, sm.prod, a0, a1);
+        }
+        publish(S, 0, gg, OP_SUM, sm.red);
+        publish(S, 1, a1, OP_SUM, sm.red);
+        set_ops(sm, OP_SUM, OP_SUM);
+        grid_sync(S);
+        collect(S, 2, sm.ops, sm.out);
+        double ng = sqrt(sm.out[0]);
+        st.orth = (ng == 0.0 || P.fro == 0.0) ? 0.0 : sqrt(sm.out[1]) / (P.fro * ng);
+    } else if (a.op == 4) {
+        double a0 = 0.0, a1 = 0.0;
+        spmv(P.A, a.in, epi_plain(P.rhs), sm.prod, a0, a1);
+        grid_sync(S);
+        inner_solve(P, S, sm, st, a.fixed_iters);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.result->inner_iters = st.inner_iters;
+        a.result->n_solves = st.n_solves;
+        a.result->n_refinements = st.n_refinements;
+        a.result->status = st.status;
+        a.result->orth = st.orth;
+    }
+}
+
+// ---------------------------------------------------------------- modified dogleg
+struct DoglegArgs {
+    ProjView P;
+    SyncView S;
+    CsrView Araw, Atraw;         // un-normalised A and A'
+    int n, m;
+    const double *b, *lb, *ub;
+    int has_box;
+    double radius;
+    double *newton, *cauchy, *g, *x1, *x2, *out;   // n
+    double *mtmp;                                    // m
+    ProjArgs::Result *result;
+};
+
+// modified_dogleg (qp_subproblem.py:320-413), whole routine in one launch.
+__global__ void __launch_bounds__(THREADS)
+k_dogleg(const DoglegArgs a) {
+    __shared__ Smem sm;
+    ProjStats st = {0, 0, 0, 0, 0.0, 0.0};
+    const SyncView &S = a.S;
+    const int n = a.n, m = a.m;
+    const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+    double a0, a1;
+    // newton = -Y b  (:368)
+    double nn = row_space(a.P, S, sm, st, a.b, -1.0, a.newton);
+    // inside box and ball? (:370-373)
+    double out = 0.0;
+    if (a.has_box)
+        for (int i = gt; i < n; i += nt) {
+            double v = a.newton[i];
+            if (v < a.lb[i] || v > a.ub[i]) out = 1.0;
+        }
+    publish(S, 0, out, OP_MAX, sm.red);
+    set_ops(sm, OP_MAX);
+    grid_sync(S);
+    collect(S, 1, sm.ops, sm.out);
+    const double *res = a.newton;
+    if (!(sm.out[0] > 0.0) && sqrt(nn) <= a.radius) {
+        res = a.newton;
+    } else {
+        // g = A' b (:376); A g (:379); cauchy = -(g.g)/(Ag.Ag) g (:380)
+        a0 = a1 = 0.0;
+        Epi eg = epi_plain(a.g); eg.want_sq = 1;
+        spmv(a.Atraw, a.b, eg, sm.prod, a0, a1);
+        publish(S, 0, a1, OP_SUM, sm.red);
+        grid_sync(S);
+        Epi eag = epi_plain(a.mtmp); eag.want_sq = 1;
+        a0 = a1 = 0.0;
+        spmv(a.Araw, a.g, eag, sm.prod, a0, a1);
+        publish(S, 1, a1, OP_SUM, sm.red);
+        set_ops(sm, OP_SUM, OP_SUM);
+        grid_sync(S);
+        collect(S, 2, sm.ops, sm.out);
+        double coef = -sm.out[0] / sm.out[1];
+        // cauchy, and step = newton - cauchy kept in x2 for now
+        for (int i = gt; i < n; i += nt) {
+            double cp = coef * a.g[i];
+            a.cauchy[i] = cp;
+            a.x2[i] = a.newton[i] - cp;
+        }
+        grid_sync(S);
+        // segment cauchy -> newton (:386-391)
+        Interval I = box_ball(S, sm, n, a.cauchy, a.x2, 1.0, a.lb, a.ub, a.has_box,
+                              a.radius, 0);
+        if (I.hit) {
+            for (int i = gt; i < n; i += nt) a.x1[i] = a.cauchy[i] + I.tb * a.x2[i];
+        } else {
+            // segment origin -> cauchy (:395-399): z = 0
+            for (int i = gt; i < n; i += nt) a.g[i] = 0.0;     // g reused as origin
+            grid_sync(S);
+            Interval J = box_ball(S, sm, n, a.g, a.cauchy, 1.0, a.lb, a.ub, a.has_box,
+                                  a.radius, 0);
+            for (int i = gt; i < n; i += nt) a.x1[i] = 0.0 + J.tb * a.cauchy[i];
+        }
+        // segment origin -> newton (:403-407)
+        for (int i = gt; i < n; i += nt) a.g[i] = 0.0;
+        grid_sync(S);
+        Interval K = box_ball(S, sm, n, a.g, a.newton, 1.0, a.lb, a.ub, a.has_box,
+                              a.radius, 0);
+        for (int i = gt; i < n; i += nt) a.x2[i] = 0.0 + K.tb * a.newton[i];
+        grid_sync(S);
+        // ||A x1 + b|| < ||A x2 + b|| ? (:410-413)
+        Epi e1 = epi_plain(a.mtmp); e1.addv = a.b; e1.sb = 1.0; e1.want_sq = 1;
+        a0 = a1 = 0.0;
+        spmv(a.Araw, a.x1, e1, sm.prod, a0, a1);
+        publish(S, 0, a1, OP_SUM, sm.red);
+        grid_sync(S);
+        a0 = a1 = 0.0;
+        spmv(a.Araw, a.x2, e1, sm.prod, a0, a1);
+        publish(S, 1, a1, OP_SUM, sm.red);
+        set_ops(sm, OP_SUM, OP_SUM);
+        grid_sync(S);
+        collect(S, 2, sm.ops, sm.out);
+        res = (sqrt(sm.out[0]) < sqrt(sm.out[1])) ? a.x1 : a.x2;
+    }
+    for (int i = gt; i < n; i += nt) a.out[i] = res[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.result->inner_iters = st.inner_iters;
+        a.result->n_solves = st.n_solves;
+        a.result->n_refinements = st.n_refinements;
+        a.result->status = st.status;
+        a.result->orth = 0.0;
+    }
+    (void)m;
+}
+
+// ---------------------------------------------------------------- intersections
+struct IntersectArgs {
+    SyncView S;
+    int n;
+    const double *z, *d, *lb, *ub;
+    int has_box, line;
+    double radius;
+    struct Result { double ta, tb; int hit; } *result;
+};
+
+// box_sphere_intersections / box_intersections / sphere_intersections
+// (qp_subproblem.py:66-303) for host callers (the SQP second-order
+// correction, equality_constrained_sqp.py:177).
+__global__ void __launch_bounds__(THREADS)
+k_intersect(const IntersectArgs a) {
+    __shared__ Smem sm;
+    Interval I = box_ball(a.S, sm, a.n, a.z, a.d, 1.0, a.lb, a.ub, a.has_box,
+                          a.radius, a.line);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.result->ta = I.ta; a.result->tb = I.tb; a.result->hit = I.hit;
+    }
+}
+
+// ---------------------------------------------------------------- plain products
+struct MatvecArgs {
+    int kind;                    // 0: CSR, 1: Hessian
+    CsrView M;
+    HessView H;
+    SyncView S;
+    const double *x;
+    double *y;
+};
+
+__global__ void __launch_bounds__(THREADS)
+k_matvec(const MatvecArgs a) {
+    __shared__ Smem sm;
+    double a0 = 0.0, a1 = 0.0;
+    if (a.kind == 0) spmv(a.M, a.x, epi_plain(a.y), sm.prod, a0, a1);
+    else hess_apply(a.H, a.S, a.x, a.y, nullptr, sm.prod, a0);
+}
+
+// ---------------------------------------------------------------- setup kernels
+// (ordinary launches, not on the per-iteration path)
+__global__ void k_row_norms(int rows, const int *rowptr, const double *val,
+                            double *dnorm2, double *dscale) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double s = 0.0;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) s += val[k] * val[k];
+    dnorm2[r] = s;
+    dscale[r] = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
+}
+
+__global__ void k_scale_rows(int rows, const int *rowptr, const double *val,
+                             const double *dscale, double *out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double d = dscale[r];
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) out[k] = val[k] * d;
+}
+
+__global__ void k_gather(long long nnz, const int *perm, const double *src,
+                         double *dst) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < nnz) dst[i] = src[perm[i]];
+}
+
+__global__ void k_gather_int(long long n, const int *perm, const int *src,
+                             int *dst) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[perm[i]];
+}
+
+__global__ void k_expand_rows(int rows, const int *rowptr, int *rowidx) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) rowidx[k] = r;
+}
+
+__global__ void k_count_cols(long long nnz, const int *col, int *counts) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < nnz) atomicAdd(&counts[col[i] + 1], 1);
+}
+
+__global__ void k_iota(long long n, int *out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)i;
+}
+
+__global__ void k_narrow_i64(long long n, const long long *in, int *out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)in[i];
+}
+
+}  // namespace ipb

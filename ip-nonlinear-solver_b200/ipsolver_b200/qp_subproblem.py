@@ -1,0 +1,168 @@
+"""Device-backed trust-region EQP routines -- the reference's
+``ipsolver/_large_scale_constrained/qp_subproblem.py`` interface (same names,
+argument meaning and error behaviour), each call one persistent CUDA kernel.
+
+``projected_cg`` runs the whole CG-Steihaug loop (H products, null-space
+projections with their inner CG on ``A A'``, reductions, sphere/box
+intersections, termination logic) on the device; only ``x`` and the ``info``
+scalars return.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sps
+from scipy.sparse.linalg import LinearOperator
+
+from .device import Context, DeviceHessian, _bounds
+from ._cabi import dptr, f64
+from .projections import DeviceMap
+
+__all__ = [
+    'sphere_intersections', 'box_intersections', 'box_sphere_intersections',
+    'inside_box_boundaries', 'reinforce_box_boundaries', 'modified_dogleg',
+    'projected_cg', 'HessianOperator', 'as_device_hessian',
+]
+
+
+# ------------------------------------------------------------------ Hessian
+class HessianOperator(LinearOperator):
+    """Lagrangian Hessian as a LinearOperator that *carries its terms* so it
+    can be applied on the device (the reference's operator is an opaque
+    closure, ``_canonical_constraint.py:119-139``; SURVEY.md finding 6).
+
+        H v = [ (sum of sparse terms + sum of dense terms) v_x ; diag_tail * v_s ]
+
+    ``terms`` are scipy sparse matrices / ndarrays of shape (n_x, n_x);
+    ``diag_tail`` holds the ``S Hs S`` diagonal of the barrier subproblem
+    (``tr_interior_point.py:206-241``).  Sparse terms are summed into one CSR
+    and dense terms into one array on the host before the upload, so the
+    device does one SpMV and/or one GEMV per product.
+    """
+
+    def __init__(self, n, terms=(), diag_tail=None, ctx=None):
+        self.n = int(n)
+        self.diag_tail = None if diag_tail is None else f64(diag_tail)
+        self.n_x = self.n - (0 if self.diag_tail is None else self.diag_tail.shape[0])
+        super().__init__(dtype=np.float64, shape=(self.n, self.n))
+        sparse_sum, dense_sum = None, None
+        for t in terms:
+            if sps.issparse(t):
+                t = sps.csr_matrix(t, dtype=np.float64)
+                sparse_sum = t if sparse_sum is None else sparse_sum + t
+            else:
+                t = np.atleast_2d(np.asarray(t, dtype=np.float64))
+                dense_sum = t if dense_sum is None else dense_sum + t
+        self.sparse = sparse_sum
+        self.dense = dense_sum
+        self._ctx = ctx
+        self._dev = None
+
+    @property
+    def device(self):
+        if self._dev is None:
+            ctx = self._ctx or Context.default()
+            self._dev = DeviceHessian(ctx, self.n, self.n_x, csr=self.sparse,
+                                      dense=self.dense, diag_tail=self.diag_tail)
+        return self._dev
+
+    def _matvec(self, x):
+        return self.device.matvec(np.asarray(x, dtype=np.float64).reshape(-1))
+
+
+def as_device_hessian(H, n):
+    """Device Hessian for anything with an explicit matrix form."""
+    if isinstance(H, HessianOperator):
+        return H.device
+    if isinstance(H, DeviceHessian):
+        return H
+    if sps.issparse(H) or isinstance(H, np.ndarray):
+        return HessianOperator(n, [H]).device
+    raise TypeError(
+        "projected_cg needs H with explicit terms (HessianOperator, scipy "
+        "sparse matrix or ndarray) to run on the device; got %s. Opaque "
+        "LinearOperators (finite-difference Hessians) are host callbacks and "
+        "are outside this path." % type(H).__name__)
+
+
+# ------------------------------------------------------------------ intersections
+def _intersections(z, d, lb, ub, trust_radius, entire_line):
+    ctx = Context.default()
+    z = f64(z)
+    d = f64(d, z.shape[0])
+    if lb is not None or ub is not None:
+        n = z.shape[0]
+        lb = np.full(n, -np.inf) if lb is None else f64(lb, n)
+        ub = np.full(n, np.inf) if ub is None else f64(ub, n)
+    ta, tb, hit = C.c_double(), C.c_double(), C.c_int()
+    ctx.check(ctx.lib.ipb_box_sphere_intersections(
+        ctx.h, z.shape[0], dptr(z), dptr(d), dptr(lb), dptr(ub),
+        float(trust_radius), int(bool(entire_line)),
+        C.byref(ta), C.byref(tb), C.byref(hit)))
+    return ta.value, tb.value, bool(hit.value)
+
+
+def sphere_intersections(z, d, trust_radius, entire_line=False):
+    """Reference ``qp_subproblem.py:66-149``."""
+    return _intersections(z, d, None, None, trust_radius, entire_line)
+
+
+def box_intersections(z, d, lb, ub, entire_line=False):
+    """Reference ``qp_subproblem.py:152-234``."""
+    return _intersections(z, d, lb, ub, np.inf, entire_line)
+
+
+def box_sphere_intersections(z, d, lb, ub, trust_radius, entire_line=False,
+                             extra_info=False):
+    """Reference ``qp_subproblem.py:237-303``."""
+    ta, tb, hit = _intersections(z, d, lb, ub, trust_radius, entire_line)
+    if not extra_info:
+        return ta, tb, hit
+    ta_s, tb_s, hit_s = _intersections(z, d, None, None, trust_radius, entire_line)
+    ta_b, tb_b, hit_b = _intersections(z, d, lb, ub, np.inf, entire_line)
+    return (ta, tb, hit, {'ta': ta_s, 'tb': tb_s, 'intersect': hit_s},
+            {'ta': ta_b, 'tb': tb_b, 'intersect': hit_b})
+
+
+def inside_box_boundaries(x, lb, ub):
+    """Reference ``qp_subproblem.py:306-308`` (host-side scalar test used by
+    the outer loop on vectors it already holds)."""
+    return bool((lb <= x).all() and (x <= ub).all())
+
+
+def reinforce_box_boundaries(x, lb, ub):
+    """Reference ``qp_subproblem.py:310-317``."""
+    return np.minimum(np.maximum(x, lb), ub)
+
+
+# ------------------------------------------------------------------ solvers
+def _projector_of(*ops):
+    binding = None
+    for op in ops:
+        if not isinstance(op, DeviceMap):
+            raise TypeError(
+                "Z and Y must come from ipsolver_b200.projections.projections() "
+                "(got %s); there is no host fallback." % type(op).__name__)
+        if binding is None:
+            binding = op.binding
+        elif op.binding is not binding:
+            raise ValueError("Z and Y belong to different projections() calls")
+    return binding.ensure()
+
+
+def modified_dogleg(A, Y, b, trust_radius, lb, ub):
+    """Reference ``qp_subproblem.py:320-413``; ``A`` must be the matrix ``Y``
+    was built from (it is taken from the device projector)."""
+    proj = _projector_of(Y)
+    return proj.modified_dogleg(b, trust_radius, lb, ub)
+
+
+def projected_cg(H, c, Z, Y, b, trust_radius=np.inf, lb=None, ub=None,
+                 tol=None, max_iter=None, max_infeasible_iter=None,
+                 return_all=False):
+    """Reference ``qp_subproblem.py:416-643``.  Raises ``ValueError`` in the
+    two situations the reference does (:517, :560)."""
+    proj = _projector_of(Z, Y)
+    c = np.asarray(c, dtype=np.float64)
+    Hd = as_device_hessian(H, c.shape[0])
+    return proj.projected_cg(Hd, c, b, trust_radius, lb, ub, tol, max_iter,
+                             max_infeasible_iter, return_all)

@@ -1,0 +1,340 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the
+golden vectors produced by the reference.  Needs a B200: ``pytest -m gpu``.
+
+Tolerances (north_star): iteration counts within +-1, vectors within 1e-8
+relative in fp64; SpMV row sums are compared bit-for-bit with scipy.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import cases
+import oracle
+from ipsolver_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from ipsolver_b200 import device, projections, qp_subproblem
+
+    class NS:
+        pass
+    ns = NS()
+    ns.device = device
+    ns.ctx = device.Context.default()
+    ns.projections = projections.projections
+    ns.orthogonality = projections.orthogonality
+    ns.qp = qp_subproblem
+    return ns
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    with open(os.path.join(golden_dir, "kat.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="module")
+def synth(golden_dir):
+    return np.load(os.path.join(golden_dir, "synth_pcg.npz"))
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    den = max(np.linalg.norm(b), 1e-300)
+    return np.linalg.norm(a - b) / den
+
+
+def assert_close(a, b, rtol=RTOL, floor=1e-12):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape
+    assert np.linalg.norm(a - b) <= rtol * np.linalg.norm(b) + floor, \
+        "rel err %.3e" % relerr(a, b)
+
+
+# ------------------------------------------------------------------ products
+@pytest.mark.parametrize("pattern", ["window", "rand"])
+@pytest.mark.parametrize("n", [10, 1000, 200000])
+def test_spmv_bit_exact(dev, pattern, n):
+    """A.x, A'.y and H.p: same left-to-right row sums as scipy's csr_matvec
+    (no FMA contraction), so the results are bit-identical."""
+    H, A, c, b = synthetic.make_qp(n, pattern, 1e4, seed=0)
+    dA = dev.device.DeviceCSR(dev.ctx, A, with_transpose=True)
+    dH = dev.device.DeviceCSR(dev.ctx, H, with_transpose=False)
+    assert np.array_equal(dA.matvec(c), A.dot(c))
+    At = A.T.tocsr()
+    At.sort_indices()
+    assert np.array_equal(dA.rmatvec(b), At.dot(b))
+    assert np.array_equal(dH.matvec(c), H.dot(c))
+    assert dA.fro_norm() == pytest.approx(sps.linalg.norm(A, 'fro'), rel=1e-14)
+
+
+def test_spmv_ragged_and_empty(dev):
+    """Empty rows, a dense row longer than one staging chunk, int64 indices,
+    an empty matrix and unsorted / duplicate entries."""
+    rng = np.random.RandomState(3)
+    n = 9000
+    M = sps.random(500, n, density=0.002, random_state=rng, format='lil')
+    M[7, :] = rng.standard_normal(n)          # 9000 nnz > CHUNK
+    M[8, :] = 0
+    M[499, :] = 0
+    M = M.tocsr()
+    x, y = rng.standard_normal(n), rng.standard_normal(500)
+    d = dev.device.DeviceCSR(dev.ctx, M)
+    assert_close(d.matvec(x), M.dot(x), 1e-14)
+    assert_close(d.rmatvec(y), M.T.dot(y), 1e-14)
+    M64 = sps.csr_matrix((M.data, M.indices.astype(np.int64),
+                          M.indptr.astype(np.int64)), shape=M.shape)
+    d64 = dev.device.DeviceCSR(dev.ctx, M64)
+    assert np.array_equal(d64.matvec(x), d.matvec(x))
+    E = sps.csr_matrix((0, 12))
+    dE = dev.device.DeviceCSR(dev.ctx, E)
+    assert dE.matvec(np.ones(12)).shape == (0,)
+    assert np.array_equal(dE.rmatvec(np.zeros(0)), np.zeros(12))
+    dup = sps.coo_matrix(([1.0, 2.0, 3.0], ([0, 0, 1], [2, 2, 0])), shape=(2, 3))
+    dd = dev.device.DeviceCSR(dev.ctx, dup)
+    assert np.array_equal(dd.matvec(np.array([1.0, 1.0, 1.0])), [3.0, 3.0])
+
+
+def test_hessian_operator_terms(dev):
+    """Sparse + dense + diagonal-tail Hessian (barrier form,
+    reference tr_interior_point.py:222-241)."""
+    rng = np.random.RandomState(5)
+    nx, ns = 300, 40
+    S = synthetic.banded_spd_hessian(nx, 10.0)
+    D = rng.standard_normal((nx, nx))
+    tail = rng.uniform(0.5, 2.0, ns)
+    v = rng.standard_normal(nx + ns)
+    for terms in ([S], [D], [S, D], [S, S.T, D]):
+        Hop = dev.qp.HessianOperator(nx + ns, terms, diag_tail=tail)
+        want = np.hstack([sum(t.dot(v[:nx]) for t in terms), tail * v[nx:]])
+        assert_close(Hop.dot(v), want, 1e-13)
+    Hop = dev.qp.HessianOperator(nx, [S])
+    assert np.array_equal(Hop.dot(v[:nx]), S.dot(v[:nx]))
+    Hz = dev.qp.HessianOperator(nx + ns, [], diag_tail=tail)
+    assert_close(Hz.dot(v), np.hstack([np.zeros(nx), tail * v[nx:]]), 1e-15)
+
+
+# ------------------------------------------------------------------ projectors
+@pytest.mark.parametrize("method", ["AugmentedSystem", "NormalEquation", None])
+def test_projectors_3x8(dev, kat, method):
+    """Reference tests/test_projections.py:25-85 on the device."""
+    A_dense = np.array(cases.A38, float)
+    A = sps.csc_matrix(A_dense)
+    Z, LS, Y = dev.projections(A, method)
+    for p, zref, lsref in zip(cases.P38_N, kat["proj38"]["Z"], kat["proj38"]["LS"]):
+        p = np.array(p, float)
+        z = Z.matvec(p)
+        assert_close(z, zref, 1e-9)
+        np.testing.assert_array_almost_equal(A.dot(z), 0)
+        np.testing.assert_array_almost_equal(dev.orthogonality(A, z), 0)
+        assert_close(LS.matvec(p), lsref, 1e-9)
+    for p, yref in zip(cases.P38_M, kat["proj38"]["Y"]):
+        y = Y.matvec(np.array(p, float))
+        assert_close(y, yref, 1e-9)
+        np.testing.assert_array_almost_equal(A.dot(y), p)
+    for p, oref in zip(cases.P38_N, kat["proj38"]["orth"]):
+        assert dev.orthogonality(A, np.array(p, float)) == pytest.approx(oref, rel=1e-12)
+
+
+def test_projectors_refinement(dev):
+    """Reference tests/test_projections.py:48-65: orth_tol=1e-18, max_refin=100."""
+    A = sps.csc_matrix(np.array(cases.A38, float))
+    Z, LS, _ = dev.projections(A, orth_tol=1e-18, max_refin=100)
+    for p in cases.P38_N:
+        x = Z.matvec(np.array(p, float))
+        np.testing.assert_array_almost_equal(A.dot(x), 0, decimal=14)
+        np.testing.assert_array_almost_equal(
+            oracle.orthogonality_measure(A, x), 0, decimal=16)
+
+
+def test_projectors_dense_input_and_validation(dev):
+    """Dense A (reference routes it to QR / SVD; here the same device maps),
+    and the reference's method validation (projections.py:372-387)."""
+    D = np.diag(range(1, 101)).astype(float)
+    A = np.hstack([D, D, D, D])
+    rng = np.random.RandomState(0)
+    Zo, LSo, Yo = oracle.build_projectors(A)
+    for method in (None, "QRFactorization", "SVDFactorization"):
+        Z, LS, Y = dev.projections(A, method)
+        for _ in range(3):
+            z = rng.normal(size=400)
+            assert_close(Z.dot(z), Zo.dot(z), 1e-9)
+            assert_close(LS.dot(z), LSo.dot(z), 1e-9)
+            y = rng.normal(size=100)
+            assert_close(Y.dot(y), Yo.dot(y), 1e-9)
+    with pytest.raises(ValueError):
+        dev.projections(A, "AugmentedSystem")
+    with pytest.raises(ValueError):
+        dev.projections(sps.csr_matrix(A), "QRFactorization")
+
+
+def test_projectors_no_constraints(dev):
+    """m = 0: Z is the identity (reference projections.py:368-369)."""
+    A = sps.csr_matrix((0, 7))
+    Z, LS, Y = dev.projections(A)
+    x = np.arange(7.0)
+    assert np.array_equal(Z.dot(x), x)
+    assert LS.dot(x).shape == (0,)
+    assert np.array_equal(Y.dot(np.zeros(0)), np.zeros(7))
+
+
+def test_stale_binding_reuploads(dev):
+    """Two matrices with one sparsity pattern share a device matrix; each
+    operator still acts for its own values."""
+    A1 = sps.csr_matrix(np.array(cases.A38, float))
+    A2 = A1.copy()
+    A2.data = A2.data * np.linspace(1, 2, A2.nnz)
+    Z1, _, _ = dev.projections(A1)
+    Z2, _, _ = dev.projections(A2)
+    x = np.arange(1.0, 9.0)
+    z1, z2 = Z1.dot(x), Z2.dot(x)
+    np.testing.assert_array_almost_equal(A1.dot(z1), 0)
+    np.testing.assert_array_almost_equal(A2.dot(z2), 0)
+    assert np.linalg.norm(A2.dot(z1)) > 1e-3
+
+
+@pytest.mark.parametrize("pattern", ["window", "rand"])
+def test_synthetic_projectors_and_dogleg(dev, synth, pattern):
+    n = cases.SYNTH_N
+    H, A, c, b = synthetic.make_qp(n, pattern, 1e4, seed=0)
+    Z, LS, Y = dev.projections(A)
+    assert_close(Z.dot(c), synth[pattern + "/Zc"], 1e-10)
+    assert_close(LS.dot(c), synth[pattern + "/LSc"], 1e-10)
+    assert_close(Y.dot(b), synth[pattern + "/Yb"], 1e-10)
+    info = Z.projector.last_info
+    assert info.n_solves >= 1 and info.inner_iters > 0
+    lb, ub = synthetic.box_bounds(n, 0.3)
+    for radius in (4.0, 40.0):
+        x = dev.qp.modified_dogleg(A, Y, b, radius, lb, ub)
+        assert_close(x, synth[pattern + "/dogleg_r%g" % radius])
+    x = dev.qp.modified_dogleg(A, Y, b, 6.0, np.full(n, -np.inf), np.full(n, np.inf))
+    assert_close(x, synth[pattern + "/dogleg_free"])
+
+
+# ------------------------------------------------------------------ small known answers
+@pytest.mark.parametrize("name", list(cases.PCG_CASES))
+def test_pcg_known_answers(dev, kat, name):
+    """The reference's 12 projected_cg cases (tests/test_qp_subproblem.py:430-649):
+    every stop_cond, both ValueErrors, active/inactive box, return_all."""
+    H, A, c, b, kw, exc = cases.PCG_CASES[name]
+    Hs, As = sps.csc_matrix(H), sps.csc_matrix(A)
+    Z, _, Y = dev.projections(As)
+    want = kat["pcg"][name]
+    if exc is not None:
+        with pytest.raises(exc) as ei:
+            dev.qp.projected_cg(Hs, np.array(c), Z, Y, np.array(b), **kw)
+        assert str(ei.value).startswith(want["msg"][:20])
+        return
+    x, info = dev.qp.projected_cg(Hs, np.array(c), Z, Y, np.array(b), **kw)
+    assert info["niter"] == want["niter"]
+    assert info["stop_cond"] == want["stop_cond"]
+    assert info["hits_boundary"] == want["hits_boundary"]
+    assert_close(x, want["x"])
+    if "allvecs" in want:
+        assert len(info["allvecs"]) == len(want["allvecs"])
+        for got, ref in zip(info["allvecs"], want["allvecs"]):
+            assert_close(got, ref)
+
+
+@pytest.mark.parametrize("name", list(cases.DOGLEG_CASES))
+def test_dogleg_known_answers(dev, kat, name):
+    A, b, radius, lb, ub = cases.DOGLEG_CASES[name]
+    A = np.array(A, float)
+    _, _, Y = dev.projections(A)
+    x = dev.qp.modified_dogleg(A, Y, np.array(b), radius, np.array(lb, float),
+                               np.array(ub, float))
+    assert_close(x, kat["dogleg"][name])
+
+
+def test_intersections_known_answers(dev, kat):
+    for (z, d, radius, line), want in zip(cases.BALL_CASES, kat["ball"]):
+        ta, tb, hit = dev.qp.sphere_intersections(z, d, radius, line)
+        assert hit == want[2]
+        assert (ta, tb) == pytest.approx(tuple(want[:2]), rel=1e-14, abs=1e-300)
+    k = 0
+    for (z, d, lb, ub, line), want in zip(cases.BOX_CASES, kat["box"]):
+        ta, tb, hit = dev.qp.box_intersections(z, d, lb, ub, line)
+        assert hit == want[2]
+        assert (ta, tb) == pytest.approx(tuple(want[:2]), rel=1e-14, abs=1e-300)
+        for radius in (2.5, np.inf):
+            ta, tb, hit = dev.qp.box_sphere_intersections(z, d, lb, ub, radius, line)
+            w = kat["box_ball"][k]
+            assert hit == w[2]
+            assert (ta, tb) == pytest.approx(tuple(w[:2]), rel=1e-14, abs=1e-300)
+            k += 1
+
+
+# ------------------------------------------------------------------ synthetic QPs
+@pytest.mark.parametrize("name", list(cases.SYNTH_RUNS))
+def test_synthetic_pcg_vs_golden(dev, synth, name):
+    pattern, kappa, kw, tau = cases.SYNTH_RUNS[name]
+    n = cases.SYNTH_N
+    H, A, c, b = synthetic.make_qp(n, pattern, kappa, seed=0)
+    Z, LS, Y = dev.projections(A)
+    kw = dict(kw)
+    if tau is not None:
+        kw["lb"], kw["ub"] = synthetic.box_bounds(n, tau)
+    x, info = dev.qp.projected_cg(H, c, Z, Y, b, **kw)
+    want = synth[name + "/info"]
+    assert abs(info["niter"] - want[0]) <= 1
+    assert info["stop_cond"] == want[1]
+    assert int(info["hits_boundary"]) == want[2]
+    assert_close(x, synth[name + "/x"])
+
+
+@pytest.mark.parametrize("n,pattern", [(50000, "window"), (50000, "rand"),
+                                       (300000, "window")])
+def test_pcg_vs_oracle_medium(dev, n, pattern):
+    """Seeded inputs at sizes the oracle (SuperLU) finishes in seconds."""
+    if pattern == "rand":
+        n = 20000          # SuperLU on the augmented system is cubic here
+    H, A, c, b = synthetic.make_qp(n, pattern, 1e4, seed=4)
+    lb, ub = synthetic.box_bounds(n, 2.0)
+    Zo, LSo, Yo = oracle.build_projectors(A)
+    Z, LS, Y = dev.projections(A)
+    x0 = Yo.dot(-b)
+    for kw in (dict(tol=1e-30, max_iter=25),
+               dict(trust_radius=1.05 * np.linalg.norm(x0)),
+               dict(lb=lb, ub=ub, trust_radius=3 * np.linalg.norm(x0))):
+        xo, io = oracle.eqp_projected_cg(H, c, Zo, Yo, b, **kw)
+        x, info = dev.qp.projected_cg(H, c, Z, Y, b, **kw)
+        assert abs(info["niter"] - io["niter"]) <= 1, (kw, info, io)
+        assert info["stop_cond"] == io["stop_cond"]
+        assert info["hits_boundary"] == io["hits_boundary"]
+        assert_close(x, xo)
+    assert_close(LS.dot(c), LSo.dot(c), 1e-9)
+
+
+def test_full_size_properties(dev):
+    """BASELINE size (n = 1e7, m = 5e6) through size-independent properties:
+    A z = 0 to round-off, idempotence Z(Zx) = Zx, A (Y b) = b, LS consistency,
+    and a projected-CG run whose result satisfies A x + b = 0 and decreases
+    the quadratic model monotonically with the iteration cap."""
+    n = 10_000_000
+    H, A, c, b = synthetic.make_qp(n, "window", 1e4, seed=0)
+    Z, LS, Y = dev.projections(A)
+    z = Z.dot(c)
+    nA = sps.linalg.norm(A, 'fro')
+    assert np.linalg.norm(A.dot(z)) <= 1e-12 * nA * np.linalg.norm(z)
+    assert_close(Z.dot(z), z, 1e-11)
+    y = Y.dot(b)
+    assert_close(A.dot(y), b, 1e-11)
+    v = LS.dot(c)
+    assert_close(A.T.dot(v) + z, c, 1e-11)          # c = A'v + Zc
+    prev = None
+    for k in (5, 10):
+        x, info = dev.qp.projected_cg(H, c, Z, Y, b, tol=1e-30, max_iter=k)
+        assert info["niter"] == k and info["stop_cond"] == 1
+        assert np.linalg.norm(A.dot(x) + b) <= 1e-10 * np.linalg.norm(b)
+        q = 0.5 * x.dot(H.dot(x)) + c.dot(x)
+        if prev is not None:
+            assert q < prev
+        prev = q
