@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Headline benchmark: projected-CG iterations/s on the synthetic sparse
+equality-constrained QP of BASELINE.json (n = 1e7, m = 5e6, banded SPD H,
+windowed 3-nnz/row A), one B200 (or N ranks under torchrun).
+
+A *step* is one ``projected_cg`` solve with exactly ``--iters`` CG iterations
+forced (``tol=1e-30, trust_radius=inf``) on a matrix
+already resident in HBM -- i.e. one pass of the hot path: 2 + iters
+null-space projections (each an inner CG on A A'), 1 row-space solve,
+1 + iters (+1) Hessian products and the fused vector updates, in ONE
+persistent kernel launch.
+
+  value  iterations/s with c, b, x resident in HBM (CUDA events on the
+         library's stream, around the K steps)
+  e2e    the same through the reference-facing Python API ``projected_cg(H, c,
+         Z, Y, b, ...)`` with pinned HOST vectors: H2D of c and b, D2H of x and
+         the info struct inside the timed region (wall clock, synchronous API)
+  roofline   algorithmic bytes of the launch (formulas of
+         SURVEY.md section 8d applied to the launch's own counters) / the
+         launch's device time, against the measured HBM copy bandwidth
+  cpu_baseline   the oracle (scipy SuperLU + numpy restatement of the
+         reference path) on a bounded sample, host cores
+
+``--impl reference`` times only the CPU path (oracle port; the reference is
+pure Python and cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "ip-nonlinear-solver_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "projected_cg_iterations_per_s"
+UNIT = "it/s"
+
+
+def algorithmic_bytes(n, m, nnzH, nnzA, niter, inner_iters, n_z, n_refin, n_hp):
+    """Compulsory HBM bytes of one launch:
+    B_spmv = 12 nnz + 4 (rows+1) + 8 cols + 8 rows; inner CG iteration
+    B_in = B_A + B_At + 56 m; one Z apply = B_A + B_At + 8 n (+ its inner
+    iterations) + B_A for the orthogonality product, again per refinement;
+    outer iteration = B_H + 72 n (+ its Z apply)."""
+    B_H = 12 * nnzH + 4 * (n + 1) + 16 * n
+    B_A = 12 * nnzA + 4 * (m + 1) + 8 * n + 8 * m
+    B_At = 12 * nnzA + 4 * (n + 1) + 8 * m + 8 * n
+    B_in = B_A + B_At + 56 * m
+    total = inner_iters * B_in
+    total += (n_z + n_refin) * (2 * B_A + B_At + 8 * n)
+    total += n_hp * B_H + niter * 72 * n
+    return total, dict(B_H=B_H, B_A=B_A, B_At=B_At, B_in=B_in)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(smax))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        t = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        t = 1
+    return t
+
+
+def cpu_reference_run(n, iters, steps, warmup, pattern, kappa):
+    """The reference's CPU path, restated by oracle/ (scipy SuperLU for
+    AugmentedSystem, numpy level-1, scipy csr_matvec): factorisation outside
+    the timed region, ``steps`` forced-iteration solves inside."""
+    import oracle
+    from ipsolver_b200 import synthetic
+    H, A, c, b = synthetic.make_qp(n, pattern, kappa, seed=0)
+    t0 = time.perf_counter()
+    Z, LS, Y = oracle.build_projectors(A)
+    t_factor = time.perf_counter() - t0
+    for _ in range(warmup):
+        oracle.eqp_projected_cg(H, c, Z, Y, b, tol=1e-30, max_iter=iters)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        _, info = oracle.eqp_projected_cg(H, c, Z, Y, b, tol=1e-30, max_iter=iters)
+        done += info["niter"]
+    dt = time.perf_counter() - t0
+    return done / dt, dt, t_factor
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_s = args.cpu_n
+    its, dt, t_factor = cpu_reference_run(n_s, args.iters, args.steps, args.warmup,
+                                          args.pattern, args.kappa)
+    scale = n_s / args.n       # per-iteration cost of the CPU path is O(n)
+    value = its * scale
+    sample = ("oracle port of the reference path (scipy SuperLU AugmentedSystem + "
+              "numpy), n=%d m=%d window A, %d forced iterations/step; the "
+              "reference cannot factorise n=%d (SuperLU int32 malloc failure), so "
+              "it/s is scaled by n_sample/n = %.3g (its per-iteration cost is "
+              "linear in n for the banded pattern); factorisation %.1f s outside "
+              "the timed region" % (n_s, n_s // 2, args.iters, args.n, scale, t_factor))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(args.steps, 1) / scale,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(),
+                         "kind": "port", "sample": sample,
+                         "measured_it_per_s_at_sample": its,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "synthetic sparse convex equality-constrained QP "
+                        "(BASELINE.json metric config): n=%d, m=%d, H banded SPD "
+                        "5 nnz/row cond=%g, A %s 3 nnz/row; projected_cg with "
+                        "%d forced iterations per step (tol=1e-30, radius=inf), "
+                        "NormalEquation projector via inner CG rtol=%g"
+                        % (args.n, args.n // 2, args.kappa, args.pattern,
+                           args.iters, args.inner_rtol),
+            "n": args.n, "m": args.n // 2, "iters_per_step": args.iters,
+            "pattern": args.pattern, "inner_rtol": args.inner_rtol,
+            "l2": "working set per inner iteration (~0.94 GB at n=1e7) exceeds "
+                  "the 126 MB L2; no explicit flush",
+            "parallelism": "1 GPU" if args.gpus == 1 else "row-partitioned x%d" % args.gpus}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def run_b200(args):
+    import torch
+    from ipsolver_b200 import synthetic, device
+    from ipsolver_b200.projections import projections, set_inner_options
+    from ipsolver_b200.qp_subproblem import projected_cg, HessianOperator
+
+    if args.gpus != 1:
+        raise SystemExit("multi-GPU row partition: see bench_multi (not in this round's "
+                         "first slice); run with --gpus 1")
+    rank = 0
+    n, m = args.n, args.n // 2
+    set_inner_options(inner_rtol=args.inner_rtol)
+    t0 = time.perf_counter()
+    H, A, c, b = synthetic.make_qp(n, args.pattern, args.kappa, seed=0)
+    t_gen = time.perf_counter() - t0
+    ctx = device.Context.default()
+    t0 = time.perf_counter()
+    Z, LS, Y = projections(A)                  # upload A, build A' on device
+    Hop = HessianOperator(n, [H])
+    Hd = Hop.device                            # upload H
+    ctx.sync()
+    t_setup = time.perf_counter() - t0
+    proj = Z.projector
+
+    # ---- value: inputs resident in HBM
+    dc, db = device.DeviceVector(ctx, c), device.DeviceVector(ctx, b)
+    dx = device.DeviceVector(ctx, length=n)
+    for _ in range(args.warmup):
+        device.projected_cg_dev(proj, Hd, dc, db, dx, tol=1e-30, max_iter=args.iters)
+    sampler = ClockSampler(ctx.device)
+    sampler.start()
+    launches0 = ctx.launches
+    kernel_ms, infos = [], []
+    ctx.timer_start()
+    for _ in range(args.steps):
+        info = device.projected_cg_dev(proj, Hd, dc, db, dx, tol=1e-30,
+                                       max_iter=args.iters)
+        kernel_ms.append(info.kernel_ms)
+        infos.append(info)
+    total_ms = ctx.timer_stop()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    niter = sum(int(i.niter) for i in infos)
+    value = niter / (total_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (the persistent solve kernel)
+    i0 = infos[-1]
+    has_b = 1
+    n_z = int(i0.n_solves) - int(i0.n_refinements) - has_b
+    bytes_launch, parts = algorithmic_bytes(
+        n, m, H.nnz, A.nnz, int(i0.niter), int(i0.inner_iters), n_z,
+        int(i0.n_refinements), int(i0.n_spmv_h))
+    avg_ms = float(np.mean(kernel_ms))
+    peak, peak_src = peaks()
+    achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_projected_cg_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_projected_cg (persistent cooperative)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_launch,
+                "avg_launch_ms": avg_ms,
+                "inner_iters_per_launch": int(i0.inner_iters),
+                "inner_iters_per_projection": int(i0.inner_iters) / max(int(i0.n_solves), 1),
+                "bytes_model": parts}
+
+    # inner CG iteration in isolation (same device code, fixed count)
+    inner_ms = device.bench_inner_iterations(proj, dc, 50)
+    inner_ms = device.bench_inner_iterations(proj, dc, 50)
+    roofline["inner_iteration_us"] = 1e3 * inner_ms / 51
+    roofline["inner_iteration_GBs"] = parts["B_in"] / (inner_ms * 1e-3 / 51) / 1e9
+
+    # ---- e2e: host vectors through the public API
+    hc = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    hb = torch.empty(m, dtype=torch.float64).pin_memory().numpy()
+    hc[:] = c
+    hb[:] = b
+    x_e2e, _ = projected_cg(Hop, hc, Z, Y, hb, tol=1e-30, max_iter=args.iters)
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(args.steps):
+        x_e2e, inf = projected_cg(Hop, hc, Z, Y, hb, tol=1e-30, max_iter=args.iters)
+        e2e_iters += inf["niter"]
+    t_e2e = time.perf_counter() - t0
+    e2e = {"value": e2e_iters / t_e2e, "unit": UNIT,
+           "h2d_bytes_per_step": 8 * (n + m), "d2h_bytes_per_step": 8 * n + 96,
+           "ms_per_step": 1e3 * t_e2e / args.steps,
+           "note": "projected_cg(H, c, Z, Y, b, ...) with pinned host c, b; x returned "
+                   "as a numpy array; A and H uploaded once (setup_s)"}
+    # the result must be the same as the device-resident run
+    xd = dx.download()
+    same = float(np.linalg.norm(xd - x_e2e) / max(np.linalg.norm(xd), 1e-300))
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1)
+    cpu = None
+    if not args.no_cpu:
+        its, dt, t_factor = cpu_reference_run(args.cpu_n, args.iters, args.cpu_steps, 0,
+                                              args.pattern, args.kappa)
+        scale = args.cpu_n / n
+        cpu = {"value": its * scale, "unit": UNIT, "cores": host_threads(),
+               "kind": "port",
+               "sample": "oracle (scipy SuperLU AugmentedSystem + numpy) at n=%d, "
+                         "%d steps x %d forced iterations, %.1f s timed + %.1f s "
+                         "factorisation; scaled by n_sample/n=%.3g to this workload "
+                         "(the reference cannot factorise n=1e7: SuperLU int32 malloc "
+                         "failure)" % (args.cpu_n, args.cpu_steps, args.iters, dt,
+                                       t_factor, scale),
+               "measured_it_per_s_at_sample": its, "host_cpus": os.cpu_count()}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "setup_s": {"generate": t_gen, "upload_and_transpose": t_setup},
+        "grid": dict(zip(("blocks", "threads", "sms"), ctx.grid())),
+        "e2e_vs_resident_rel_diff": same,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--iters", type=int, default=8)
+    ap.add_argument("--pattern", default="window")
+    ap.add_argument("--kappa", type=float, default=1e4)
+    ap.add_argument("--inner-rtol", type=float, default=1e-13)
+    ap.add_argument("--cpu-n", type=int, default=1_000_000)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -196,6 +196,10 @@ int64_t ipb_vec_len(const ipb_vec *v);
 void *ipb_vec_ptr(ipb_vec *v);   /* raw device pointer (for torch interop) */
 
 /* ---- measurement helpers (bench.py) -------------------------------------- */
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of
+ * this library is launched on; torch.cuda.Event would not see it). */
+int ipb_timer_start(ipb_ctx *ctx);
+int ipb_timer_stop(ipb_ctx *ctx, double *ms);
 /* Runs ``iters`` inner CG iterations on A A' (fixed count, no convergence
  * test) starting from rhs = A x; returns device milliseconds.  This is the
  * dominant loop of the path, timed in isolation. */

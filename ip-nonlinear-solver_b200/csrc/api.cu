@@ -55,7 +55,7 @@ struct ipb_proj {
 struct ipb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     int sms = 0, blocks = 0;
     unsigned *barrier = nullptr;
     double *partials = nullptr;
@@ -207,6 +207,8 @@ extern "C" int ipb_ctx_create(int device, ipb_ctx **out) {
     CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(ctx, cudaEventCreate(&ctx->ev0));
     CU(ctx, cudaEventCreate(&ctx->ev1));
+    CU(ctx, cudaEventCreate(&ctx->ev2));
+    CU(ctx, cudaEventCreate(&ctx->ev3));
     int occ = 0, o;
     CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_projected_cg, THREADS, 0));
     occ = o;
@@ -242,6 +244,8 @@ extern "C" int ipb_ctx_destroy(ipb_ctx *ctx) {
     cudaFree(ctx->ws); cudaFree(ctx->stage); cudaFree(ctx->cub_tmp);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return IPB_OK;
@@ -263,6 +267,23 @@ extern "C" int64_t ipb_ctx_launches(const ipb_ctx *ctx) { return ctx ? ctx->laun
 
 extern "C" int ipb_ctx_sync(ipb_ctx *ctx) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+extern "C" int ipb_timer_start(ipb_ctx *ctx) {
+    if (!ctx) return IPB_ERR_INVALID;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+    return IPB_OK;
+}
+
+extern "C" int ipb_timer_stop(ipb_ctx *ctx, double *ms) {
+    if (!ctx || !ms) return IPB_ERR_INVALID;
+    float f = 0.f;
+    CU(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+    CU(ctx, cudaEventSynchronize(ctx->ev3));
+    CU(ctx, cudaEventElapsedTime(&f, ctx->ev2, ctx->ev3));
+    *ms = f;
     return IPB_OK;
 }
 
@@ -620,6 +641,7 @@ static ProjView proj_view(const ipb_proj *p) {
     v.m = p->A->rows; v.n = p->A->cols;
     v.A = csr_view(p->A, p->nval);
     v.At = csr_view_t(p->A, p->nt_val);
+    v.Araw = p->A->val;
     v.dscale = p->dscale; v.dnorm2 = p->dnorm2;
     v.fro = p->fro; v.orth_tol = p->orth_tol; v.max_refin = p->max_refin;
     v.rtol = p->rtol; v.maxit = p->maxit;

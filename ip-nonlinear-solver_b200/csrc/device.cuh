@@ -60,6 +60,7 @@ struct ProjView {
     int m, n;
     CsrView A;                // row-normalised A  (At = its transpose)
     CsrView At;
+    const double *Araw;       // un-normalised values of A (same pattern)
     const double *dscale;     // 1/||a_i|| (0 for empty rows)
     const double *dnorm2;     // ||a_i||^2
     double fro;               // ||A||_F of the un-normalised A
@@ -168,13 +169,14 @@ struct Epi {
     double sa, sb;
     const double *dotv;
     const double *wv;
+    const double *post;       // stored value is y_r * post[r] (sums use y_r)
     int want_sq;
     int accumulate;
 };
 
 __device__ __forceinline__ Epi epi_plain(double *y) {
     Epi e; e.y = y; e.addv = nullptr; e.sa = 1.0; e.sb = 0.0; e.dotv = nullptr;
-    e.wv = nullptr; e.want_sq = 0; e.accumulate = 0; return e;
+    e.wv = nullptr; e.post = nullptr; e.want_sq = 0; e.accumulate = 0; return e;
 }
 
 __device__ __forceinline__ void row_out(const Epi &e, int r, double s,
@@ -183,9 +185,9 @@ __device__ __forceinline__ void row_out(const Epi &e, int r, double s,
     if (e.sa != 1.0) y = e.sa * y;
     if (e.addv) y = y + e.sb * e.addv[r];
     if (e.accumulate) y = e.y[r] + y;
-    e.y[r] = y;
     if (e.dotv) acc0 += y * e.dotv[r];
     if (e.want_sq) acc1 += (e.wv ? e.wv[r] * (y * y) : y * y);
+    e.y[r] = e.post ? y * e.post[r] : y;
 }
 
 // y = M x over all row blocks of M (grid-stride).  prod: CHUNK doubles smem.
@@ -444,12 +446,14 @@ __device__ __noinline__ double null_space(const ProjView &P, const SyncView &S,
             publish(S, 0, a1, OP_SUM, sm.red);
         }
         grid_sync(S);
-        // w~ = A~ z (next right-hand side), ||A z||^2 = sum d_i w~_i^2
+        // w = A z with the un-normalised A, exactly what orthogonality()
+        // measures (projections.py:52); D^-1/2 w is the next right-hand side
         {
             Epi e = epi_plain(P.rhs);
-            e.want_sq = 1; e.wv = P.dnorm2;
+            e.want_sq = 1; e.post = P.dscale;
+            CsrView Ar = P.A; Ar.val = P.Araw;
             a0 = a1 = 0.0;
-            spmv(P.A, z, e, sm.prod, a0, a1);
+            spmv(Ar, z, e, sm.prod, a0, a1);
             publish(S, 1, a1, OP_SUM, sm.red);
         }
         set_ops(sm, OP_SUM, OP_SUM);
@@ -651,7 +655,7 @@ k_projected_cg(const PcgArgs a) {
     int status = 0, stop_cond = 1, hits = 0;
     long long k = 0;
     double tol = a.tol;
-    double acc0, acc1;
+    double acc0;
     int x_slot = 0;
 
     // ---- x = Y(-b)  (:502); exactly 0 when b == 0, as in the reference
@@ -713,7 +717,6 @@ k_projected_cg(const PcgArgs a) {
     if (max_iter > nm) max_iter = nm;
     long long max_inf = a.max_infeasible < 0 ? nm : a.max_infeasible;
     long long counter = 0;
-    bool have_feas = false;
 
     if (!done) {
         // last_feasible_x: zeros (the reference leaves it uninitialised, :547)
@@ -776,7 +779,6 @@ k_projected_cg(const PcgArgs a) {
                     for (int i = gt; i < n; i += nt)
                         a.xfeas[i] = clipd(x[i] + ta * p[i], a.lb[i], a.ub[i]);
                     counter = 0;
-                    have_feas = true;
                 }
             }
             if (counter > max_inf) break;                            // :615-616
@@ -815,7 +817,6 @@ k_projected_cg(const PcgArgs a) {
         collect(S, 1, sm.ops, sm.out);
         if (sm.out[0] > 0.0) { final_slot = 2; hits = 1; }
     }
-    (void)have_feas;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         PcgArgs::Result &R = *a.result;
         R.niter = k; R.stop_cond = stop_cond; R.hits_boundary = hits;
@@ -862,8 +863,9 @@ k_projector(const ProjArgs a) {
         for (int i = gt; i < P.n; i += nt) { double v = a.in[i]; gg += v * v; }
         if (P.m > 0) {
             Epi e = epi_plain(P.rhs);
-            e.want_sq = 1; e.wv = P.dnorm2;
-            spmv(P.A, a.in, e, sm.prod, a0, a1);
+            e.want_sq = 1;
+            CsrView Ar = P.A; Ar.val = P.Araw;
+            spmv(Ar, a.in, e, sm.prod, a0, a1);
         }
         publish(S, 0, gg, OP_SUM, sm.red);
         publish(S, 1, a1, OP_SUM, sm.red);

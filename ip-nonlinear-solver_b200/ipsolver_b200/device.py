@@ -65,6 +65,14 @@ class Context:
     def sync(self):
         self.check(self.lib.ipb_ctx_sync(self.h))
 
+    def timer_start(self):
+        self.check(self.lib.ipb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self.check(self.lib.ipb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
 
 class DeviceVector:
     def __init__(self, ctx, data=None, length=None):
@@ -300,6 +308,30 @@ class DeviceProjector:
             k = min(info.n_allvecs, cap)
             out['allvecs'] = [allvecs[i*self.n:(i+1)*self.n].copy() for i in range(k)]
         return x, out
+
+
+def projected_cg_dev(proj, H, c, b, x, trust_radius=np.inf, lb=None, ub=None,
+                     tol=None, max_iter=None, max_infeasible_iter=None):
+    """Device-resident variant: c, b, lb, ub, x are DeviceVectors; only the
+    info struct crosses PCIe."""
+    ctx = proj.ctx
+    info = PcgInfo()
+    st = ctx.lib.ipb_projected_cg_dev(
+        ctx.h, H.h, proj.h, c.h, b.h, float(trust_radius),
+        lb.h if lb is not None else None, ub.h if ub is not None else None,
+        -1.0 if tol is None else float(tol),
+        -1 if max_iter is None else int(max_iter),
+        -1 if max_infeasible_iter is None else int(max_infeasible_iter),
+        x.h, C.byref(info))
+    ctx.check(st)
+    return info
+
+
+def bench_inner_iterations(proj, x, iters):
+    ms = C.c_double()
+    proj.ctx.check(proj.ctx.lib.ipb_bench_inner_iterations(
+        proj.ctx.h, proj.h, x.h, int(iters), C.byref(ms)))
+    return ms.value
 
 
 def _bounds(lb, ub, n):
