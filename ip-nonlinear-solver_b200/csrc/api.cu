@@ -27,11 +27,13 @@ struct ipb_csr {
     int64_t nnz = 0;
     int *rowptr = nullptr, *col = nullptr;
     double *val = nullptr;
-    int rpt = 1;
+    int4 *desc = nullptr;
+    int nblk = 0;
     bool has_t = false;
     int *t_rowptr = nullptr, *t_col = nullptr, *perm = nullptr;
     double *t_val = nullptr;
-    int t_rpt = 1;
+    int4 *t_desc = nullptr;
+    int t_nblk = 0;
 };
 
 struct ipb_hess {
@@ -118,7 +120,7 @@ static SyncView sync_view(const ipb_ctx *ctx) {
 
 static CsrView csr_view(const ipb_csr *m, const double *val_override = nullptr) {
     CsrView v;
-    v.rows = m->rows; v.cols = m->cols; v.rpt = m->rpt;
+    v.rows = m->rows; v.cols = m->cols; v.nblk = m->nblk; v.desc = m->desc;
     v.rowptr = m->rowptr; v.col = m->col;
     v.val = val_override ? val_override : m->val;
     return v;
@@ -126,24 +128,52 @@ static CsrView csr_view(const ipb_csr *m, const double *val_override = nullptr) 
 
 static CsrView csr_view_t(const ipb_csr *m, const double *val_override = nullptr) {
     CsrView v;
-    v.rows = m->cols; v.cols = m->rows; v.rpt = m->t_rpt;
+    v.rows = m->cols; v.cols = m->rows; v.nblk = m->t_nblk; v.desc = m->t_desc;
     v.rowptr = m->t_rowptr; v.col = m->t_col;
     v.val = val_override ? val_override : m->t_val;
     return v;
 }
 
-static int pick_rpt(int64_t rows, int64_t nnz) {
-    if (rows <= 0) return 1;
-    double avg = std::max(1e-9, (double)nnz / (double)rows);
-    int rpt = (int)std::floor(0.92 * CHUNK / (avg * THREADS));
-    return std::max(1, std::min(RPT_MAX, rpt));
-}
+// Cut the rows of a CSR matrix into blocks of at most CHUNK nnz and RMAX rows
+// (greedy, in row order); a row longer than CHUNK becomes a block of its own.
+// rowptr is read back from the device (once per sparsity pattern).
+static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, int rows, int4 **d_desc, int *nblk);
 
 // number of CTAs for a launch working on ``work`` items: enough to fill the
 // machine for large problems, a handful for tiny ones (cheap barriers).
 static int grid_for(const ipb_ctx *ctx, int64_t work) {
     int64_t want = (work + THREADS * 4 - 1) / (THREADS * 4);
     return (int)std::max<int64_t>(1, std::min<int64_t>(ctx->blocks, want));
+}
+
+static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, int rows, int4 **d_desc, int *nblk) {
+    std::vector<int> rp((size_t)rows + 1);
+    CU(ctx, cudaMemcpyAsync(rp.data(), d_rowptr, ((size_t)rows + 1) * sizeof(int),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int4> desc;
+    desc.reserve((size_t)rows / 256 + 16);
+    int r0 = 0;
+    while (r0 < rows) {
+        int r1 = r0 + 1;
+        const int base = rp[r0];
+        if (rp[r1] - base <= CHUNK) {
+            const int rlim = std::min(rows, r0 + RMAX);
+            // largest r1 with rp[r1] - base <= CHUNK (rp is non-decreasing)
+            int hi = (int)(std::upper_bound(rp.begin() + r1, rp.begin() + rlim + 1,
+                                            base + CHUNK) - rp.begin()) - 1;
+            r1 = std::max(r1, hi);
+        }
+        desc.push_back(make_int4(r0, r1, base, rp[r1] - base));
+        r0 = r1;
+    }
+    *nblk = (int)desc.size();
+    CHECK(dalloc(ctx, d_desc, desc.size()));
+    if (!desc.empty())
+        CU(ctx, cudaMemcpyAsync(*d_desc, desc.data(), desc.size() * sizeof(int4),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
 }
 
 template <typename Args>
@@ -153,7 +183,7 @@ static int launch_coop(ipb_ctx *ctx, void (*kernel)(const Args), const Args &arg
     void *params[] = {(void *)&args};
     if (ms) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CU(ctx, cudaLaunchCooperativeKernel((void *)kernel, dim3(grid), dim3(THREADS),
-                                        params, 0, ctx->stream));
+                                        params, sizeof(Smem), ctx->stream));
     ctx->launches += 1;
     if (ms) {
         CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -209,17 +239,16 @@ extern "C" int ipb_ctx_create(int device, ipb_ctx **out) {
     CU(ctx, cudaEventCreate(&ctx->ev1));
     CU(ctx, cudaEventCreate(&ctx->ev2));
     CU(ctx, cudaEventCreate(&ctx->ev3));
-    int occ = 0, o;
-    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_projected_cg, THREADS, 0));
-    occ = o;
-    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_projector, THREADS, 0));
-    occ = std::min(occ, o);
-    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_dogleg, THREADS, 0));
-    occ = std::min(occ, o);
-    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_matvec, THREADS, 0));
-    occ = std::min(occ, o);
-    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_intersect, THREADS, 0));
-    occ = std::min(occ, o);
+    int occ = 1 << 30, o;
+    const void *kernels[] = {(const void *)k_projected_cg, (const void *)k_projector,
+                             (const void *)k_dogleg, (const void *)k_matvec,
+                             (const void *)k_intersect};
+    for (const void *k : kernels) {
+        CU(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(Smem)));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k, THREADS, sizeof(Smem)));
+        occ = std::min(occ, o);
+    }
     if (occ < 1) IPB_FAIL(ctx, IPB_ERR_CUDA, "kernels do not fit on an SM");
     int per_sm = occ;
     const char *env = getenv("IPB_BLOCKS_PER_SM");
@@ -319,9 +348,9 @@ extern "C" void *ipb_vec_ptr(ipb_vec *v) { return v ? v->d : nullptr; }
 static int build_transpose(ipb_ctx *ctx, ipb_csr *m) {
     const int64_t nnz = m->nnz;
     const int TB = 256;
-    CHECK(dalloc(ctx, &m->t_rowptr, (size_t)m->cols + 1));
-    CHECK(dalloc(ctx, &m->t_col, (size_t)nnz));
-    CHECK(dalloc(ctx, &m->t_val, (size_t)nnz));
+    CHECK(dalloc(ctx, &m->t_rowptr, (size_t)m->cols + 1 + PAD));
+    CHECK(dalloc(ctx, &m->t_col, (size_t)nnz + PAD));
+    CHECK(dalloc(ctx, &m->t_val, (size_t)nnz + PAD));
     CHECK(dalloc(ctx, &m->perm, (size_t)nnz));
     CU(ctx, cudaMemsetAsync(m->t_rowptr, 0, ((size_t)m->cols + 1) * sizeof(int), ctx->stream));
     if (nnz > 0) {
@@ -357,9 +386,9 @@ static int build_transpose(ipb_ctx *ctx, ipb_csr *m) {
         CU(ctx, cub::DeviceScan::InclusiveSum(ctx->cub_tmp, tmp, m->t_rowptr, m->t_rowptr,
                                               m->cols + 1, ctx->stream));
     }
-    m->t_rpt = pick_rpt(m->cols, nnz);
-    m->has_t = true;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CHECK(build_blocks(ctx, m->t_rowptr, m->cols, &m->t_desc, &m->t_nblk));
+    m->has_t = true;
     return IPB_OK;
 }
 
@@ -374,11 +403,10 @@ extern "C" int ipb_csr_create(ipb_ctx *ctx, int64_t rows, int64_t cols, int64_t 
     CU(ctx, cudaSetDevice(ctx->device));
     ipb_csr *m = new ipb_csr();
     m->rows = (int)rows; m->cols = (int)cols; m->nnz = nnz;
-    m->rpt = pick_rpt(rows, nnz);
     int s;
-    if ((s = dalloc(ctx, &m->rowptr, (size_t)rows + 1)) != IPB_OK) return s;
-    if ((s = dalloc(ctx, &m->col, (size_t)nnz)) != IPB_OK) return s;
-    if ((s = dalloc(ctx, &m->val, (size_t)nnz)) != IPB_OK) return s;
+    if ((s = dalloc(ctx, &m->rowptr, (size_t)rows + 1 + PAD)) != IPB_OK) return s;
+    if ((s = dalloc(ctx, &m->col, (size_t)nnz + PAD)) != IPB_OK) return s;
+    if ((s = dalloc(ctx, &m->val, (size_t)nnz + PAD)) != IPB_OK) return s;
     if (index_bytes == 4) {
         CU(ctx, cudaMemcpyAsync(m->rowptr, indptr, ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
         if (nnz) CU(ctx, cudaMemcpyAsync(m->col, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -400,6 +428,7 @@ extern "C" int ipb_csr_create(ipb_ctx *ctx, int64_t rows, int64_t cols, int64_t 
     if (nnz) CU(ctx, cudaMemcpyAsync(m->val, data, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (rows == 0) CU(ctx, cudaMemsetAsync(m->rowptr, 0, sizeof(int), ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((s = build_blocks(ctx, m->rowptr, m->rows, &m->desc, &m->nblk)) != IPB_OK) return s;
     if (with_transpose) {
         s = build_transpose(ctx, m);
         if (s != IPB_OK) return s;
@@ -424,8 +453,8 @@ extern "C" int ipb_csr_update_values(ipb_ctx *ctx, ipb_csr *m, const double *dat
 extern "C" int ipb_csr_destroy(ipb_ctx *ctx, ipb_csr *m) {
     (void)ctx;
     if (!m) return IPB_OK;
-    cudaFree(m->rowptr); cudaFree(m->col); cudaFree(m->val);
-    cudaFree(m->t_rowptr); cudaFree(m->t_col); cudaFree(m->t_val); cudaFree(m->perm);
+    cudaFree(m->rowptr); cudaFree(m->col); cudaFree(m->val); cudaFree(m->desc);
+    cudaFree(m->t_desc); cudaFree(m->t_rowptr); cudaFree(m->t_col); cudaFree(m->t_val); cudaFree(m->perm);
     delete m;
     return IPB_OK;
 }
@@ -613,8 +642,8 @@ extern "C" int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int ma
     p->rtol = inner_rtol > 0 ? inner_rtol : 1e-13;
     p->maxit = inner_maxit > 0 ? inner_maxit : 1000;
     size_t m = A->rows, n = A->cols, nnz = A->nnz;
-    CHECK(dalloc(ctx, &p->nval, nnz));
-    CHECK(dalloc(ctx, &p->nt_val, nnz));
+    CHECK(dalloc(ctx, &p->nval, nnz + PAD));
+    CHECK(dalloc(ctx, &p->nt_val, nnz + PAD));
     CHECK(dalloc(ctx, &p->dscale, m));
     CHECK(dalloc(ctx, &p->dnorm2, m));
     CHECK(dalloc(ctx, &p->v, m)); CHECK(dalloc(ctx, &p->r, m)); CHECK(dalloc(ctx, &p->w, m));

@@ -26,8 +26,10 @@ namespace ipb {
 
 constexpr int THREADS = 256;          // threads per CTA of every kernel
 constexpr int WARPS = THREADS / 32;
-constexpr int CHUNK = 3072;           // products staged per pass (24 KB smem)
-constexpr int RPT_MAX = 8;            // max rows per thread in one row block
+constexpr int CHUNK = 2048;           // nnz staged per pipeline stage
+constexpr int RMAX = 1536;            // max rows of one row block
+constexpr int PAD = 8;                // over-read slack of the bulk copies (elements)
+constexpr int MIN_BLOCKS = 3;         // CTAs per SM the kernels are compiled for
 constexpr int NSLOT = 8;              // reduction slots per barrier
 constexpr int MAX_GRID = 2048;        // upper bound on CTAs of a launch
 
@@ -36,7 +38,8 @@ enum { OP_SUM = 0, OP_MIN = 1, OP_MAX = 2 };
 // ---------------------------------------------------------------- structs
 struct CsrView {
     int rows, cols;
-    int rpt;                  // rows per thread: a row block is rpt*THREADS rows
+    int nblk;                 // row blocks (built at upload, <= CHUNK nnz each)
+    const int4 *desc;         // per block {r0, r1, p0, len}
     const int *rowptr;
     const int *col;
     const double *val;
@@ -160,6 +163,61 @@ __device__ __forceinline__ void collect(const SyncView &S, int nslots,
     __syncthreads();
 }
 
+// ---------------------------------------------------------------- shared memory
+// One pipeline stage = the val / col / rowptr slices of one row block, landed
+// by three 1-D TMA bulk copies (cp.async.bulk) that complete on the stage's
+// mbarrier.  Two stages: the copy of the CTA's next row block is in flight
+// while the current one is multiplied, summed and written out.
+struct __align__(128) Stage {
+    double val[CHUNK + PAD];      // products overwrite the values in place
+    int col[CHUNK + PAD];
+    int rowptr[RMAX + PAD];
+};
+
+struct __align__(128) Smem {
+    Stage st[2];
+    unsigned long long mbar[2];
+    unsigned uses[2];             // completed uses of each stage (phase parity)
+    double red[WARPS];
+    double out[NSLOT];
+    int ops[NSLOT];
+};
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void pipeline_init(Smem &sm) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.mbar[1])));
+        sm.uses[0] = 0; sm.uses[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
+                                         unsigned long long *mbar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(mbar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, unsigned parity,
+                                          int *abort_flag) {
+    unsigned done = 0;
+    long long spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(smem_addr(mbar)), "r"(parity) : "memory");
+        if (++spins > (1ll << 26)) { *abort_flag = 2; __trap(); }
+    }
+}
+
 // ---------------------------------------------------------------- SpMV
 // Row epilogue: y_r = sa*s + sb*addv[r] (+ y_r when accumulate); optional
 // running sums  acc0 += y_r*dotv[r],  acc1 += y_r^2 * (wv ? wv[r] : 1).
@@ -190,56 +248,98 @@ __device__ __forceinline__ void row_out(const Epi &e, int r, double s,
     e.y[r] = e.post ? y * e.post[r] : y;
 }
 
-// y = M x over all row blocks of M (grid-stride).  prod: CHUNK doubles smem.
+// Row block descriptor {r0, r1, p0, len}: rows [r0, r1), nnz [p0, p0 + len).
+// Blocks are cut at upload so that len <= CHUNK and r1 - r0 <= RMAX; a row
+// longer than CHUNK is a block of its own (len > CHUNK).
+
+// Thread 0 starts the three bulk copies of a row block into stage ``s``.
+// Sources are aligned down to 4 elements (16 B for ints, 32 B for doubles)
+// and sizes rounded up to 4; the arrays are allocated with PAD slack.
+__device__ __forceinline__ void stage_issue(const CsrView &M, const int4 d,
+                                            Smem &sm, int s) {
+    if (threadIdx.x == 0 && d.w <= CHUNK) {
+        const int p0a = d.z & ~3, r0a = d.x & ~3;
+        const unsigned cnt = (unsigned)((d.z + d.w - p0a + 3) & ~3);
+        const unsigned rcnt = (unsigned)((d.y - r0a + 1 + 3) & ~3);
+        Stage &st = sm.st[s];
+        // the stage was last written by ordinary stores (products in place):
+        // order them before the async-proxy writes of the new copy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        unsigned tx = cnt * 12u + rcnt * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     ::"r"(smem_addr(&sm.mbar[s])), "r"(tx) : "memory");
+        bulk_g2s(st.val, M.val + p0a, cnt * 8u, &sm.mbar[s]);
+        bulk_g2s(st.col, M.col + p0a, cnt * 4u, &sm.mbar[s]);
+        bulk_g2s(st.rowptr, M.rowptr + r0a, rcnt * 4u, &sm.mbar[s]);
+    }
+}
+
+// y = M x over all row blocks of M (grid-stride), double-buffered: while a
+// block is processed the TMA copy of the CTA's next block is in flight and
+// the descriptor of the one after that is being fetched.
 __device__ __noinline__ void spmv(const CsrView M, const double *x, const Epi e,
-                                  double *prod, double &acc0, double &acc1) {
-    const int R = M.rpt * THREADS;
-    const int nblk = (M.rows + R - 1) / R;
+                                  Smem &sm, const SyncView &S, double &acc0,
+                                  double &acc1) {
     const int tid = threadIdx.x;
-    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int r0 = blk * R;
-        const int r1 = min(r0 + R, M.rows);
-        const int p0 = ldg_stream(M.rowptr + r0);
-        const int p1 = ldg_stream(M.rowptr + r1);
-        int rs[RPT_MAX], re[RPT_MAX];
-        double acc[RPT_MAX];
-#pragma unroll
-        for (int j = 0; j < RPT_MAX; ++j) {
-            int r = r0 + tid + j * THREADS;
-            acc[j] = 0.0;
-            if (j < M.rpt && r < r1) {
-                rs[j] = ldg_stream(M.rowptr + r);
-                re[j] = ldg_stream(M.rowptr + r + 1);
-            } else {
-                rs[j] = re[j] = p1;
+    const int G = gridDim.x;
+    int blk = blockIdx.x;
+    if (blk >= M.nblk) return;
+    int4 cur = __ldg(M.desc + blk);
+    int4 nxt = (blk + G < M.nblk) ? __ldg(M.desc + blk + G) : cur;
+    int s = 0;
+    stage_issue(M, cur, sm, s);
+    for (; blk < M.nblk; blk += G) {
+        int4 nn = (blk + 2 * G < M.nblk) ? __ldg(M.desc + blk + 2 * G) : nxt;
+        if (blk + G < M.nblk) stage_issue(M, nxt, sm, s ^ 1);
+        const int r0 = cur.x, r1 = cur.y, p0 = cur.z, len = cur.w;
+        if (len <= CHUNK) {
+            Stage &st = sm.st[s];
+            mbar_wait(&sm.mbar[s], sm.uses[s] & 1u, S.abort_flag);
+            const int p0a = p0 & ~3, r0a = r0 & ~3;
+            double *pv = st.val + (p0 - p0a);
+            const int *pc = st.col + (p0 - p0a);
+            int k = tid;
+            for (; k + 3 * THREADS < len; k += 4 * THREADS) {
+                int c0 = pc[k], c1 = pc[k + THREADS];
+                int c2 = pc[k + 2 * THREADS], c3 = pc[k + 3 * THREADS];
+                double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+                pv[k] = pv[k] * x0;
+                pv[k + THREADS] = pv[k + THREADS] * x1;
+                pv[k + 2 * THREADS] = pv[k + 2 * THREADS] * x2;
+                pv[k + 3 * THREADS] = pv[k + 3 * THREADS] * x3;
             }
-        }
-        for (int p = p0; p < p1; p += CHUNK) {
-            const int len = min(CHUNK, p1 - p);
-            // stage products, coalesced over the nnz range
-#pragma unroll 4
-            for (int k = tid; k < len; k += THREADS) {
-                double a = ldg_stream(M.val + p + k);
-                int c = ldg_stream(M.col + p + k);
-                prod[k] = a * x[c];
+            for (; k < len; k += THREADS) pv[k] = pv[k] * x[pc[k]];
+            __syncthreads();
+            if (tid == 0) sm.uses[s] += 1;
+            const double *prod = st.val - p0a;        // prod[q], q a global nnz index
+            const int *rp = st.rowptr - r0a;          // rp[r], r a global row index
+            for (int r = r0 + tid; r < r1; r += THREADS) {
+                int rs = rp[r], re = rp[r + 1];
+                double sum = 0.0;
+                for (int q = rs; q < re; ++q) sum += prod[q];
+                row_out(e, r, sum, acc0, acc1);
             }
             __syncthreads();
+        } else {
+            // one long row: the whole CTA strides over it, fixed-order tree
+            double part = 0.0;
+            for (int q = p0 + tid; q < p0 + len; q += THREADS)
+                part += ldg_stream(M.val + q) * x[ldg_stream(M.col + q)];
+            part = warp_reduce(part, OP_SUM);
+            __syncthreads();
+            if ((tid & 31) == 0) sm.red[tid >> 5] = part;
+            __syncthreads();
+            if (tid == 0) {
+                double sum = sm.red[0];
 #pragma unroll
-            for (int j = 0; j < RPT_MAX; ++j) {
-                if (j < M.rpt) {
-                    int a = max(rs[j], p) - p, b = min(re[j], p + len) - p;
-                    double s = acc[j];
-                    for (int k = a; k < b; ++k) s += prod[k];
-                    acc[j] = s;
-                }
+                for (int w = 1; w < WARPS; ++w) sum += sm.red[w];
+                row_out(e, r0, sum, acc0, acc1);
             }
             __syncthreads();
         }
-#pragma unroll
-        for (int j = 0; j < RPT_MAX; ++j) {
-            int r = r0 + tid + j * THREADS;
-            if (j < M.rpt && r < r1) row_out(e, r, acc[j], acc0, acc1);
-        }
+        cur = nxt;
+        nxt = nn;
+        s ^= 1;
     }
 }
 
@@ -269,7 +369,7 @@ __device__ __noinline__ void gemv_dense(const double *D, int nx, const double *x
 // separated by a grid barrier because row->CTA maps differ between terms.
 __device__ __noinline__ void hess_apply(const HessView &H, const SyncView &S,
                                         const double *x, double *y,
-                                        const double *dotv, double *prod,
+                                        const double *dotv, Smem &sm,
                                         double &acc0) {
     double dummy = 0.0;
     Epi e = epi_plain(y);
@@ -283,7 +383,7 @@ __device__ __noinline__ void hess_apply(const HessView &H, const SyncView &S,
         Epi es = e;
         es.accumulate = H.has_dense;
         es.dotv = dotv;
-        spmv(H.S, x, es, prod, acc0, dummy);
+        spmv(H.S, x, es, sm, S, acc0, dummy);
     }
     const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
     if (!H.has_dense && !H.has_csr) {
@@ -300,14 +400,7 @@ __device__ __noinline__ void hess_apply(const HessView &H, const SyncView &S,
     }
 }
 
-// ---------------------------------------------------------------- shared memory
-struct Smem {
-    double prod[CHUNK];
-    double red[WARPS];
-    double out[NSLOT];
-    int ops[NSLOT];
-};
-
+// ---------------------------------------------------------------- reduction ops
 __device__ __forceinline__ void set_ops(Smem &sm, int o0, int o1 = 0, int o2 = 0,
                                         int o3 = 0, int o4 = 0, int o5 = 0,
                                         int o6 = 0, int o7 = 0) {
@@ -342,13 +435,13 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
     }
     grid_sync(S);
     a0 = a1 = 0.0;
-    spmv(P.At, P.r, epi_plain(P.t), sm.prod, a0, a1);
+    spmv(P.At, P.r, epi_plain(P.t), sm, S, a0, a1);
     grid_sync(S);
     {
         Epi e = epi_plain(P.w);
         e.dotv = P.r;
         a0 = 0.0; a1 = 0.0;
-        spmv(P.A, P.t, e, sm.prod, a0, a1);
+        spmv(P.A, P.t, e, sm, S, a0, a1);
         publish(S, 0, a0, OP_SUM, sm.red);
         publish(S, 1, gpart, OP_SUM, sm.red);
     }
@@ -367,29 +460,48 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
     while (k < maxit) {
         ++k;
         gpart = 0.0;
-        for (int i = gt; i < m; i += nt) {
-            double ri = P.r[i], wi = P.w[i];
-            double pi = ri + beta * P.p[i];
-            double si = wi + beta * P.s[i];
-            P.p[i] = pi; P.s[i] = si;
-            P.v[i] = P.v[i] + alpha * pi;
-            ri = ri - alpha * si;
-            P.r[i] = ri;
-            gpart += ri * ri;
+        {
+            // fused 4-vector update, 128-bit accesses, two in flight per thread
+            const int m2 = m >> 1;
+            double2 *r2 = reinterpret_cast<double2 *>(P.r);
+            double2 *p2 = reinterpret_cast<double2 *>(P.p);
+            double2 *s2 = reinterpret_cast<double2 *>(P.s);
+            double2 *v2 = reinterpret_cast<double2 *>(P.v);
+            const double2 *w2 = reinterpret_cast<const double2 *>(P.w);
+#pragma unroll 2
+            for (int i = gt; i < m2; i += nt) {
+                double2 ri = r2[i], wi = w2[i], pi = p2[i], si = s2[i], vi = v2[i];
+                pi.x = ri.x + beta * pi.x; pi.y = ri.y + beta * pi.y;
+                si.x = wi.x + beta * si.x; si.y = wi.y + beta * si.y;
+                vi.x = vi.x + alpha * pi.x; vi.y = vi.y + alpha * pi.y;
+                ri.x = ri.x - alpha * si.x; ri.y = ri.y - alpha * si.y;
+                p2[i] = pi; s2[i] = si; v2[i] = vi; r2[i] = ri;
+                gpart += ri.x * ri.x;
+                gpart += ri.y * ri.y;
+            }
+            if ((m & 1) && gt == 0) {
+                const int i = m - 1;
+                double ri = P.r[i], wi = P.w[i];
+                double pi = ri + beta * P.p[i];
+                double si = wi + beta * P.s[i];
+                P.p[i] = pi; P.s[i] = si;
+                P.v[i] = P.v[i] + alpha * pi;
+                ri = ri - alpha * si;
+                P.r[i] = ri;
+                gpart += ri * ri;
+            }
         }
         grid_sync(S);
         a0 = a1 = 0.0;
-        spmv(P.At, P.r, epi_plain(P.t), sm.prod, a0, a1);
+        spmv(P.At, P.r, epi_plain(P.t), sm, S, a0, a1);
         grid_sync(S);
         {
             Epi e = epi_plain(P.w);
             e.dotv = P.r;
             a0 = 0.0; a1 = 0.0;
-            spmv(P.A, P.t, e, sm.prod, a0, a1);
-            double g = 0.0;
-            for (int i = gt; i < m; i += nt) { double ri = P.r[i]; g += ri * ri; }
+            spmv(P.A, P.t, e, sm, S, a0, a1);
             publish(S, 0, a0, OP_SUM, sm.red);
-            publish(S, 1, g, OP_SUM, sm.red);
+            publish(S, 1, gpart, OP_SUM, sm.red);
         }
         grid_sync(S);
         collect(S, 2, sm.ops, sm.out);
@@ -430,7 +542,7 @@ __device__ __noinline__ double null_space(const ProjView &P, const SyncView &S,
         return sm.out[0];
     }
     a0 = a1 = 0.0;
-    spmv(P.A, x, epi_plain(P.rhs), sm.prod, a0, a1);
+    spmv(P.A, x, epi_plain(P.rhs), sm, S, a0, a1);
     grid_sync(S);
     inner_solve(P, S, sm, st);
     const double *src = x;
@@ -442,7 +554,7 @@ __device__ __noinline__ double null_space(const ProjView &P, const SyncView &S,
             Epi e = epi_plain(z);
             e.sa = -1.0; e.addv = src; e.sb = 1.0; e.want_sq = 1;
             a0 = a1 = 0.0;
-            spmv(P.At, P.v, e, sm.prod, a0, a1);
+            spmv(P.At, P.v, e, sm, S, a0, a1);
             publish(S, 0, a1, OP_SUM, sm.red);
         }
         grid_sync(S);
@@ -453,7 +565,7 @@ __device__ __noinline__ double null_space(const ProjView &P, const SyncView &S,
             e.want_sq = 1; e.post = P.dscale;
             CsrView Ar = P.A; Ar.val = P.Araw;
             a0 = a1 = 0.0;
-            spmv(Ar, z, e, sm.prod, a0, a1);
+            spmv(Ar, z, e, sm, S, a0, a1);
             publish(S, 1, a1, OP_SUM, sm.red);
         }
         set_ops(sm, OP_SUM, OP_SUM);
@@ -483,7 +595,7 @@ __device__ __noinline__ void least_squares(const ProjView &P, const SyncView &S,
     const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
     if (P.m == 0) return;
     double a0 = 0.0, a1 = 0.0;
-    spmv(P.A, x, epi_plain(P.rhs), sm.prod, a0, a1);
+    spmv(P.A, x, epi_plain(P.rhs), sm, S, a0, a1);
     grid_sync(S);
     inner_solve(P, S, sm, st);
     for (int i = gt; i < P.m; i += nt) vout[i] = P.dscale[i] * P.v[i];
@@ -505,7 +617,7 @@ __device__ __noinline__ double row_space(const ProjView &P, const SyncView &S,
     Epi e = epi_plain(y);
     e.want_sq = 1;
     double a0 = 0.0, a1 = 0.0;
-    spmv(P.At, P.v, e, sm.prod, a0, a1);
+    spmv(P.At, P.v, e, sm, S, a0, a1);
     publish(S, 0, a1, OP_SUM, sm.red);
     set_ops(sm, OP_SUM);
     grid_sync(S);
@@ -642,9 +754,11 @@ __device__ __forceinline__ void store_allvec(const PcgArgs &a, int &count,
     ++count;
 }
 
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_projected_cg(const PcgArgs a) {
-    __shared__ Smem sm;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    pipeline_init(sm);
     const SyncView &S = a.S;
     const int n = a.n;
     const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
@@ -676,7 +790,7 @@ k_projected_cg(const PcgArgs a) {
     // ---- r = Z(H x + c), g = Z r, p = -g  (:503-505)
     if (bb > 0.0) {
         acc0 = 0.0;
-        hess_apply(a.H, S, x, a.tmp, nullptr, sm.prod, acc0);
+        hess_apply(a.H, S, x, a.tmp, nullptr, sm, acc0);
         ++n_spmv_h;
         grid_sync(S);
         for (int i = gt; i < n; i += nt) a.tmp[i] = a.tmp[i] + a.c[i];
@@ -692,7 +806,7 @@ k_projected_cg(const PcgArgs a) {
     store_allvec(a, nvec, x);
     // ---- H_p = H p, rt_g = ||g||^2  (:511-512)
     acc0 = 0.0;
-    hess_apply(a.H, S, p, Hp, p, sm.prod, acc0);
+    hess_apply(a.H, S, p, Hp, p, sm, acc0);
     ++n_spmv_h;
     publish(S, 0, acc0, OP_SUM, sm.red);
     set_ops(sm, OP_SUM);
@@ -793,7 +907,7 @@ k_projected_cg(const PcgArgs a) {
             rt_g = rt_g_next;                                        // :633
             grid_sync(S);
             acc0 = 0.0;                                              // :634
-            hess_apply(a.H, S, p, Hp, p, sm.prod, acc0);
+            hess_apply(a.H, S, p, Hp, p, sm, acc0);
             ++n_spmv_h;
             publish(S, 0, acc0, OP_SUM, sm.red);
             set_ops(sm, OP_SUM);
@@ -844,9 +958,11 @@ struct ProjArgs {
     } *result;
 };
 
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_projector(const ProjArgs a) {
-    __shared__ Smem sm;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    pipeline_init(sm);
     ProjStats st = {0, 0, 0, 0, 0.0, 0.0};
     const SyncView &S = a.S;
     const ProjView &P = a.P;
@@ -865,7 +981,7 @@ k_projector(const ProjArgs a) {
             Epi e = epi_plain(P.rhs);
             e.want_sq = 1;
             CsrView Ar = P.A; Ar.val = P.Araw;
-            spmv(Ar, a.in, e, sm.prod, a0, a1);
+            spmv(Ar, a.in, e, sm, S, a0, a1);
         }
         publish(S, 0, gg, OP_SUM, sm.red);
         publish(S, 1, a1, OP_SUM, sm.red);
@@ -876,7 +992,7 @@ k_projector(const ProjArgs a) {
         st.orth = (ng == 0.0 || P.fro == 0.0) ? 0.0 : sqrt(sm.out[1]) / (P.fro * ng);
     } else if (a.op == 4) {
         double a0 = 0.0, a1 = 0.0;
-        spmv(P.A, a.in, epi_plain(P.rhs), sm.prod, a0, a1);
+        spmv(P.A, a.in, epi_plain(P.rhs), sm, S, a0, a1);
         grid_sync(S);
         inner_solve(P, S, sm, st, a.fixed_iters);
     }
@@ -904,9 +1020,11 @@ struct DoglegArgs {
 };
 
 // modified_dogleg (qp_subproblem.py:320-413), whole routine in one launch.
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_dogleg(const DoglegArgs a) {
-    __shared__ Smem sm;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    pipeline_init(sm);
     ProjStats st = {0, 0, 0, 0, 0.0, 0.0};
     const SyncView &S = a.S;
     const int n = a.n, m = a.m;
@@ -932,12 +1050,12 @@ k_dogleg(const DoglegArgs a) {
         // g = A' b (:376); A g (:379); cauchy = -(g.g)/(Ag.Ag) g (:380)
         a0 = a1 = 0.0;
         Epi eg = epi_plain(a.g); eg.want_sq = 1;
-        spmv(a.Atraw, a.b, eg, sm.prod, a0, a1);
+        spmv(a.Atraw, a.b, eg, sm, S, a0, a1);
         publish(S, 0, a1, OP_SUM, sm.red);
         grid_sync(S);
         Epi eag = epi_plain(a.mtmp); eag.want_sq = 1;
         a0 = a1 = 0.0;
-        spmv(a.Araw, a.g, eag, sm.prod, a0, a1);
+        spmv(a.Araw, a.g, eag, sm, S, a0, a1);
         publish(S, 1, a1, OP_SUM, sm.red);
         set_ops(sm, OP_SUM, OP_SUM);
         grid_sync(S);
@@ -973,11 +1091,11 @@ k_dogleg(const DoglegArgs a) {
         // ||A x1 + b|| < ||A x2 + b|| ? (:410-413)
         Epi e1 = epi_plain(a.mtmp); e1.addv = a.b; e1.sb = 1.0; e1.want_sq = 1;
         a0 = a1 = 0.0;
-        spmv(a.Araw, a.x1, e1, sm.prod, a0, a1);
+        spmv(a.Araw, a.x1, e1, sm, S, a0, a1);
         publish(S, 0, a1, OP_SUM, sm.red);
         grid_sync(S);
         a0 = a1 = 0.0;
-        spmv(a.Araw, a.x2, e1, sm.prod, a0, a1);
+        spmv(a.Araw, a.x2, e1, sm, S, a0, a1);
         publish(S, 1, a1, OP_SUM, sm.red);
         set_ops(sm, OP_SUM, OP_SUM);
         grid_sync(S);
@@ -1008,9 +1126,11 @@ struct IntersectArgs {
 // box_sphere_intersections / box_intersections / sphere_intersections
 // (qp_subproblem.py:66-303) for host callers (the SQP second-order
 // correction, equality_constrained_sqp.py:177).
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_intersect(const IntersectArgs a) {
-    __shared__ Smem sm;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    pipeline_init(sm);
     Interval I = box_ball(a.S, sm, a.n, a.z, a.d, 1.0, a.lb, a.ub, a.has_box,
                           a.radius, a.line);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1028,12 +1148,14 @@ struct MatvecArgs {
     double *y;
 };
 
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_matvec(const MatvecArgs a) {
-    __shared__ Smem sm;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    pipeline_init(sm);
     double a0 = 0.0, a1 = 0.0;
-    if (a.kind == 0) spmv(a.M, a.x, epi_plain(a.y), sm.prod, a0, a1);
-    else hess_apply(a.H, a.S, a.x, a.y, nullptr, sm.prod, a0);
+    if (a.kind == 0) spmv(a.M, a.x, epi_plain(a.y), sm, a.S, a0, a1);
+    else hess_apply(a.H, a.S, a.x, a.y, nullptr, sm, a0);
 }
 
 // ---------------------------------------------------------------- setup kernels

@@ -299,22 +299,29 @@ def test_synthetic_pcg_vs_golden(dev, synth, name):
         kw["lb"], kw["ub"] = synthetic.box_bounds(n, tau)
     x, info = dev.qp.projected_cg(H, c, Z, Y, b, **kw)
     want = synth[name + "/info"]
+    ref = synth[name + "/x"]
     assert info["stop_cond"] == want[1]
     assert int(info["hits_boundary"]) == want[2]
-    # 1e-8 relative, unless the reference path itself is more sensitive than
-    # that on this input: the two *_default runs take ~175 CG iterations at
-    # cond(H) = 1e4 and the oracle's own answer moves by ~1e-5 when c is
-    # perturbed by one part in 1e16; the bound is then 20x that sensitivity.
+    # The two *_default runs take ~175 CG iterations at cond(H) = 1e4: the
+    # reference path itself is chaotic there (the oracle's answer moves by
+    # ~1e-5 when c is perturbed by one part in 1e16, and its NormalEquation
+    # variant differs from AugmentedSystem by 5 iterations and 2e-3 in x), so
+    # for those the check is on what the run converges to -- the quadratic
+    # model, feasibility, iteration count within 5 % -- not on 1e-8 in x.
     Zo, LSo, Yo = oracle.build_projectors(A)
     wiggle = 1 + 1e-16 * np.sign(np.random.RandomState(0).randn(n))
     xp, _ = oracle.eqp_projected_cg(H, c * wiggle, Zo, Yo, b, **kw)
-    sens = relerr(xp, synth[name + "/x"])
-    assert_close(x, synth[name + "/x"], max(RTOL, 20 * sens))
-    # iteration count within +-1; for the chaotic runs within 3 % (the
-    # oracle's own NormalEquation variant differs from AugmentedSystem by 5
-    # iterations on window_default)
-    slack = 1 if sens < RTOL else max(1, int(0.03 * want[0]))
-    assert abs(info["niter"] - want[0]) <= slack
+    sens = relerr(xp, ref)
+    if sens < RTOL:
+        assert abs(info["niter"] - want[0]) <= 1
+        assert_close(x, ref)
+    else:
+        def q(v):
+            return 0.5 * v.dot(H.dot(v)) + c.dot(v)
+        assert abs(info["niter"] - want[0]) <= max(1, int(0.05 * want[0]))
+        assert abs(q(x) - q(ref)) <= 1e-5 * abs(q(ref))
+        assert np.linalg.norm(A.dot(x) + b) <= 1e-10 * np.linalg.norm(b)
+        assert_close(x, ref, max(1e-2, 200 * sens))
 
 
 @pytest.mark.parametrize("n,pattern", [(50000, "window"), (50000, "rand"),
