@@ -128,7 +128,14 @@ int ipb_hess_matvec_dev(ipb_ctx *ctx, const ipb_hess *h, const ipb_vec *x, ipb_v
  * borrowed and must have been created with_transpose. */
 int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int max_refin,
                     double inner_rtol, int inner_maxit, ipb_proj **out);
-/* call after ipb_csr_update_values(A): refreshes row norms, ||A||_F, A'. */
+/* How (A A') is applied inside the inner CG: mode 0 (default) keeps the explicit
+ * product M = A A' in HBM when that moves fewer bytes per application than A and
+ * A' do (12 nnz(M) < 24 nnz(A) + 16 n), mode 1 always applies A then A', mode 2
+ * always uses M.  The pattern of M is built once per sparsity pattern, its
+ * values on every refresh.  ipb_proj_aat_nnz: nnz(M), or -1 when not held. */
+int ipb_proj_set_aat_mode(ipb_ctx *ctx, ipb_proj *p, int mode);
+int64_t ipb_proj_aat_nnz(const ipb_proj *p);
+/* call after ipb_csr_update_values(A): refreshes row norms, ||A||_F, A', M. */
 int ipb_proj_refresh(ipb_ctx *ctx, ipb_proj *p);
 int ipb_proj_destroy(ipb_ctx *ctx, ipb_proj *p);
 /* Z: z = x - A'(AA')^-1 A x with refinement (null_space closures :65-80, :114-142) */

@@ -52,6 +52,14 @@ struct ipb_proj {
     int max_refin = 3, maxit = 1000;
     double *v = nullptr, *r = nullptr, *w = nullptr, *p = nullptr, *s = nullptr,
            *rhs = nullptr, *t = nullptr;
+    // explicit M = A~ A~' (pattern built once, values per refresh)
+    int aat_mode = 0;                  // 0 auto, 1 never, 2 always
+    bool has_M = false;
+    int64_t m_nnz = 0;
+    int *m_rowptr = nullptr, *m_col = nullptr;
+    double *m_val = nullptr;
+    int4 *m_desc = nullptr;
+    int m_nblk = 0;
 };
 
 struct ipb_ctx {
@@ -611,6 +619,85 @@ extern "C" int ipb_hess_matvec_dev(ipb_ctx *ctx, const ipb_hess *h, const ipb_ve
 }
 
 // ------------------------------------------------------------------ projector
+static void free_aat(ipb_proj *p) {
+    cudaFree(p->m_rowptr); cudaFree(p->m_col); cudaFree(p->m_val); cudaFree(p->m_desc);
+    p->m_rowptr = p->m_col = nullptr; p->m_val = nullptr; p->m_desc = nullptr;
+    p->has_M = false; p->m_nnz = 0; p->m_nblk = 0;
+}
+
+// Sparsity pattern of M = A A' on the device: expand every pair of rows that
+// share a column into a 64-bit (row, col) key, radix-sort, unique.  The
+// explicit product is kept only when it moves fewer bytes per application
+// than A and A' do (12 nnz(M) against 24 nnz(A) + 16 n), unless forced.
+static int build_aat_pattern(ipb_ctx *ctx, ipb_proj *p) {
+    free_aat(p);
+    ipb_csr *A = p->A;
+    const int m = A->rows, n = A->cols;
+    if (p->aat_mode == 1 || m == 0 || A->nnz == 0) return IPB_OK;
+    const int TB = 256;
+    long long *cnt = nullptr, *ptr = nullptr;
+    CHECK(dalloc(ctx, &cnt, (size_t)m + 1));
+    CHECK(dalloc(ctx, &ptr, (size_t)m + 1));
+    CU(ctx, cudaMemsetAsync(cnt, 0, ((size_t)m + 1) * sizeof(long long), ctx->stream));
+    k_aat_count<<<cdiv(m, TB), TB, 0, ctx->stream>>>(m, A->rowptr, A->col, A->t_rowptr, cnt);
+    ctx->launches += 1;
+    size_t tmp = 0;
+    CU(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, ptr, m + 1, ctx->stream));
+    CHECK(ensure_cub(ctx, tmp));
+    CU(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, tmp, cnt, ptr, m + 1, ctx->stream));
+    long long ncand = 0;
+    CU(ctx, cudaMemcpyAsync(&ncand, ptr + m, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const long long budget = 2 * (long long)A->nnz + n;     // nnz(M) that still pays
+    const long long cap = p->aat_mode == 2 ? (1ll << 31) - 2 : 8 * budget;
+    if (ncand > cap || ncand >= (1ll << 31) - 1) {
+        cudaFree(cnt); cudaFree(ptr);
+        if (p->aat_mode == 2)
+            IPB_FAIL(ctx, IPB_ERR_NOMEM, "explicit A A' would have %lld candidate entries", ncand);
+        return IPB_OK;
+    }
+    unsigned long long *keys = nullptr, *keys2 = nullptr;
+    int *d_num = nullptr;
+    CHECK(dalloc(ctx, &keys, (size_t)ncand));
+    CHECK(dalloc(ctx, &keys2, (size_t)ncand));
+    CHECK(dalloc(ctx, &d_num, 1));
+    k_aat_expand<<<cdiv(m, TB), TB, 0, ctx->stream>>>(m, A->rowptr, A->col, A->t_rowptr,
+                                                      A->t_col, ptr, keys);
+    ctx->launches += 1;
+    int bits = 1;
+    while ((1ll << bits) < (long long)m && bits < 31) ++bits;
+    CU(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys, keys2, (int)ncand, 0, 32 + bits,
+                                           ctx->stream));
+    CHECK(ensure_cub(ctx, tmp));
+    CU(ctx, cub::DeviceRadixSort::SortKeys(ctx->cub_tmp, tmp, keys, keys2, (int)ncand, 0, 32 + bits,
+                                           ctx->stream));
+    CU(ctx, cub::DeviceSelect::Unique(nullptr, tmp, keys2, keys, d_num, (int)ncand, ctx->stream));
+    CHECK(ensure_cub(ctx, tmp));
+    CU(ctx, cub::DeviceSelect::Unique(ctx->cub_tmp, tmp, keys2, keys, d_num, (int)ncand, ctx->stream));
+    int nnzM = 0;
+    CU(ctx, cudaMemcpyAsync(&nnzM, d_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    int status = IPB_OK;
+    if (p->aat_mode == 2 || (long long)nnzM <= budget) {
+        p->m_nnz = nnzM;
+        if ((status = dalloc(ctx, &p->m_rowptr, (size_t)m + 1 + PAD)) == IPB_OK &&
+            (status = dalloc(ctx, &p->m_col, (size_t)nnzM + PAD)) == IPB_OK &&
+            (status = dalloc(ctx, &p->m_val, (size_t)nnzM + PAD)) == IPB_OK) {
+            k_aat_rows<<<cdiv((long long)nnzM + 1, TB), TB, 0, ctx->stream>>>(
+                nnzM, m, keys, p->m_rowptr, p->m_col);
+            ctx->launches += 1;
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); status = IPB_ERR_CUDA; }
+            if (status == IPB_OK)
+                status = build_blocks(ctx, p->m_rowptr, m, &p->m_desc, &p->m_nblk);
+            if (status == IPB_OK) p->has_M = true;
+        }
+        if (status != IPB_OK) free_aat(p);
+    }
+    cudaFree(cnt); cudaFree(ptr); cudaFree(keys); cudaFree(keys2); cudaFree(d_num);
+    return status;
+}
+
 extern "C" int ipb_proj_refresh(ipb_ctx *ctx, ipb_proj *p) {
     if (!ctx || !p) return IPB_ERR_INVALID;
     ipb_csr *A = p->A;
@@ -623,6 +710,11 @@ extern "C" int ipb_proj_refresh(ipb_ctx *ctx, ipb_proj *p) {
         ctx->launches += 2;
         if (A->nnz) {
             k_gather<<<cdiv(A->nnz, 256), 256, 0, ctx->stream>>>(A->nnz, A->perm, p->nval, p->nt_val);
+            ctx->launches += 1;
+        }
+        if (p->has_M) {
+            k_aat_values<<<cdiv(A->rows, 128), 128, 0, ctx->stream>>>(
+                A->rows, A->rowptr, A->col, p->nval, p->m_rowptr, p->m_col, p->m_val);
             ctx->launches += 1;
         }
         CHECK(device_sum(ctx, p->dnorm2, A->rows, &s));
@@ -649,9 +741,23 @@ extern "C" int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int ma
     CHECK(dalloc(ctx, &p->v, m)); CHECK(dalloc(ctx, &p->r, m)); CHECK(dalloc(ctx, &p->w, m));
     CHECK(dalloc(ctx, &p->p, m)); CHECK(dalloc(ctx, &p->s, m)); CHECK(dalloc(ctx, &p->rhs, m));
     CHECK(dalloc(ctx, &p->t, n));
+    const char *env = getenv("IPB_EXPLICIT_AAT");      // 0 auto, 1 never, 2 always
+    if (env) p->aat_mode = atoi(env);
+    CHECK(build_aat_pattern(ctx, p));
     CHECK(ipb_proj_refresh(ctx, p));
     *out = p;
     return IPB_OK;
+}
+
+extern "C" int ipb_proj_set_aat_mode(ipb_ctx *ctx, ipb_proj *p, int mode) {
+    if (!ctx || !p || mode < 0 || mode > 2) return IPB_ERR_INVALID;
+    p->aat_mode = mode;
+    CHECK(build_aat_pattern(ctx, p));
+    return ipb_proj_refresh(ctx, p);
+}
+
+extern "C" int64_t ipb_proj_aat_nnz(const ipb_proj *p) {
+    return (p && p->has_M) ? p->m_nnz : -1;
 }
 
 extern "C" int ipb_proj_destroy(ipb_ctx *ctx, ipb_proj *p) {
@@ -660,6 +766,7 @@ extern "C" int ipb_proj_destroy(ipb_ctx *ctx, ipb_proj *p) {
     cudaFree(p->nval); cudaFree(p->nt_val); cudaFree(p->dscale); cudaFree(p->dnorm2);
     cudaFree(p->v); cudaFree(p->r); cudaFree(p->w); cudaFree(p->p); cudaFree(p->s);
     cudaFree(p->rhs); cudaFree(p->t);
+    free_aat(p);
     delete p;
     return IPB_OK;
 }
@@ -670,6 +777,11 @@ static ProjView proj_view(const ipb_proj *p) {
     v.m = p->A->rows; v.n = p->A->cols;
     v.A = csr_view(p->A, p->nval);
     v.At = csr_view_t(p->A, p->nt_val);
+    v.has_M = p->has_M ? 1 : 0;
+    if (p->has_M) {
+        v.M.rows = v.m; v.M.cols = v.m; v.M.nblk = p->m_nblk; v.M.desc = p->m_desc;
+        v.M.rowptr = p->m_rowptr; v.M.col = p->m_col; v.M.val = p->m_val;
+    }
     v.Araw = p->A->val;
     v.dscale = p->dscale; v.dnorm2 = p->dnorm2;
     v.fro = p->fro; v.orth_tol = p->orth_tol; v.max_refin = p->max_refin;

@@ -63,6 +63,8 @@ struct ProjView {
     int m, n;
     CsrView A;                // row-normalised A  (At = its transpose)
     CsrView At;
+    CsrView M;                // explicit A~ A~' (m x m), valid when has_M
+    int has_M;
     const double *Araw;       // un-normalised values of A (same pattern)
     const double *dscale;     // 1/||a_i|| (0 for empty rows)
     const double *dnorm2;     // ||a_i||^2
@@ -412,6 +414,24 @@ __device__ __forceinline__ void set_ops(Smem &sm, int o0, int o1 = 0, int o2 = 0
 }
 
 // ---------------------------------------------------------------- inner CG
+// w = (A~ A~') r with  acc0 += w.r : one SpMV with the explicit product M
+// when the projector holds it (half the matrix bytes and no n-vector
+// round trip), otherwise A~ (A~' r) through P.t with a barrier in between.
+__device__ __forceinline__ void normal_apply(const ProjView &P, const SyncView &S,
+                                             Smem &sm, double &acc0) {
+    double dummy = 0.0;
+    Epi e = epi_plain(P.w);
+    e.dotv = P.r;
+    if (P.has_M) {
+        spmv(P.M, P.r, e, sm, S, acc0, dummy);
+    } else {
+        spmv(P.At, P.r, epi_plain(P.t), sm, S, acc0, dummy);
+        grid_sync(S);
+        acc0 = 0.0;
+        spmv(P.A, P.t, e, sm, S, acc0, dummy);
+    }
+}
+
 // Solve (A~ A~') v = rhs, A~ the row-normalised A, rhs in P.rhs, v in P.v.
 // Chronopoulos-Gear single-reduction CG:
 //   r = rhs; w = M r; gamma = r.r; delta = r.w; alpha = gamma/delta; beta = 0
@@ -434,17 +454,10 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
         gpart += ri * ri;
     }
     grid_sync(S);
-    a0 = a1 = 0.0;
-    spmv(P.At, P.r, epi_plain(P.t), sm, S, a0, a1);
-    grid_sync(S);
-    {
-        Epi e = epi_plain(P.w);
-        e.dotv = P.r;
-        a0 = 0.0; a1 = 0.0;
-        spmv(P.A, P.t, e, sm, S, a0, a1);
-        publish(S, 0, a0, OP_SUM, sm.red);
-        publish(S, 1, gpart, OP_SUM, sm.red);
-    }
+    a0 = 0.0;
+    normal_apply(P, S, sm, a0);
+    publish(S, 0, a0, OP_SUM, sm.red);
+    publish(S, 1, gpart, OP_SUM, sm.red);
     set_ops(sm, OP_SUM, OP_SUM);
     grid_sync(S);
     collect(S, 2, sm.ops, sm.out);
@@ -492,17 +505,10 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
             }
         }
         grid_sync(S);
-        a0 = a1 = 0.0;
-        spmv(P.At, P.r, epi_plain(P.t), sm, S, a0, a1);
-        grid_sync(S);
-        {
-            Epi e = epi_plain(P.w);
-            e.dotv = P.r;
-            a0 = 0.0; a1 = 0.0;
-            spmv(P.A, P.t, e, sm, S, a0, a1);
-            publish(S, 0, a0, OP_SUM, sm.red);
-            publish(S, 1, gpart, OP_SUM, sm.red);
-        }
+        a0 = 0.0;
+        normal_apply(P, S, sm, a0);
+        publish(S, 0, a0, OP_SUM, sm.red);
+        publish(S, 1, gpart, OP_SUM, sm.red);
         grid_sync(S);
         collect(S, 2, sm.ops, sm.out);
         double delta2 = sm.out[0], gamma2 = sm.out[1];
@@ -1209,6 +1215,68 @@ __global__ void k_iota(long long n, int *out) {
 __global__ void k_narrow_i64(long long n, const long long *in, int *out) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) out[i] = (int)in[i];
+}
+
+// ---- explicit M = A A' (pattern once per sparsity pattern, values per update)
+// Candidate count of row i: sum over its columns j of the column's length.
+__global__ void k_aat_count(int rows, const int *rowptr, const int *col,
+                            const int *t_rowptr, long long *cnt) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    long long c = 0;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+        int j = col[k];
+        c += t_rowptr[j + 1] - t_rowptr[j];
+    }
+    cnt[r] = c;
+}
+
+// keys[cand_ptr[i] + ...] = (i << 32) | k for every row k that shares a column with row i
+__global__ void k_aat_expand(int rows, const int *rowptr, const int *col,
+                             const int *t_rowptr, const int *t_col,
+                             const long long *cand_ptr, unsigned long long *keys) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    long long o = cand_ptr[r];
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+        int j = col[k];
+        for (int q = t_rowptr[j]; q < t_rowptr[j + 1]; ++q)
+            keys[o++] = ((unsigned long long)(unsigned)r << 32) | (unsigned)t_col[q];
+    }
+}
+
+// CSR arrays of M from its sorted unique (row, col) keys
+__global__ void k_aat_rows(long long nnz, int rows, const unsigned long long *keys,
+                           int *rowptr, int *col) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i > nnz) return;
+    int row = i < nnz ? (int)(keys[i] >> 32) : rows;
+    int prev = i > 0 ? (int)(keys[i - 1] >> 32) : -1;
+    for (int r = prev + 1; r <= row; ++r) rowptr[r] = (int)i;
+    if (i < nnz) col[i] = (int)(keys[i] & 0xffffffffull);
+}
+
+// M[i,k] = sum_j a_ij a_kj, j ascending (rows of A are sorted): both M[i,k]
+// and M[k,i] come out bit-identical.
+__global__ void k_aat_values(int rows, const int *rowptr, const int *col,
+                             const double *val, const int *m_rowptr,
+                             const int *m_col, double *m_val) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const int a0 = rowptr[i], a1 = rowptr[i + 1];
+    for (int e = m_rowptr[i]; e < m_rowptr[i + 1]; ++e) {
+        const int k = m_col[e];
+        int p = a0, q = rowptr[k];
+        const int q1 = rowptr[k + 1];
+        double s = 0.0;
+        while (p < a1 && q < q1) {
+            int cp = col[p], cq = col[q];
+            if (cp == cq) { s += val[p] * val[q]; ++p; ++q; }
+            else if (cp < cq) ++p;
+            else ++q;
+        }
+        m_val[e] = s;
+    }
 }
 
 }  // namespace ipb
