@@ -213,6 +213,12 @@ int ipb_timer_stop(ipb_ctx *ctx, double *ms);
 int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x,
                                int iters, double *ms);
 
+/* Repeats ONE phase of the inner iteration ``reps`` times inside one launch,
+ * a grid barrier after each (0: fused vector update, 1: A' r, 2: A t, 3: M r,
+ * 4: barrier only); returns device milliseconds.  Results are discarded and
+ * the projector's work vectors are overwritten. */
+int ipb_bench_phase(ipb_ctx *ctx, ipb_proj *p, int phase, int reps, double *ms);
+
 #ifdef __cplusplus
 }
 #endif

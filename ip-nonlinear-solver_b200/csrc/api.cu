@@ -879,6 +879,14 @@ extern "C" int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_v
     return IPB_OK;
 }
 
+extern "C" int ipb_bench_phase(ipb_ctx *ctx, ipb_proj *p, int phase, int reps, double *ms) {
+    if (!ctx || !p || reps <= 0 || phase < 0 || phase > 4) return IPB_ERR_INVALID;
+    ipb_proj_info info;
+    CHECK(run_proj(ctx, p, 10 + phase, p->rhs, nullptr, reps, &info));
+    if (ms) *ms = info.kernel_ms;
+    return IPB_OK;
+}
+
 // ------------------------------------------------------------------ projected CG
 static int run_pcg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, const double *dc,
                    const double *db, double radius, const double *dlb, const double *dub,

@@ -1001,6 +1001,42 @@ k_projector(const ProjArgs a) {
         spmv(P.A, a.in, epi_plain(P.rhs), sm, S, a0, a1);
         grid_sync(S);
         inner_solve(P, S, sm, st, a.fixed_iters);
+    } else if (a.op >= 10) {
+        // one phase of the inner iteration repeated fixed_iters times, each
+        // followed by a grid barrier (measurement only; results discarded)
+        const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+        double a0 = 0.0, a1 = 0.0;
+        for (int it = 0; it < a.fixed_iters; ++it) {
+            if (a.op == 10) {
+                const int m2 = P.m >> 1;
+                double2 *r2 = reinterpret_cast<double2 *>(P.r);
+                double2 *p2 = reinterpret_cast<double2 *>(P.p);
+                double2 *s2 = reinterpret_cast<double2 *>(P.s);
+                double2 *v2 = reinterpret_cast<double2 *>(P.v);
+                const double2 *w2 = reinterpret_cast<const double2 *>(P.w);
+                const double alpha = 1e-3, beta = 0.5;
+#pragma unroll 2
+                for (int i = gt; i < m2; i += nt) {
+                    double2 ri = r2[i], wi = w2[i], pi = p2[i], si = s2[i], vi = v2[i];
+                    pi.x = ri.x + beta * pi.x; pi.y = ri.y + beta * pi.y;
+                    si.x = wi.x + beta * si.x; si.y = wi.y + beta * si.y;
+                    vi.x = vi.x + alpha * pi.x; vi.y = vi.y + alpha * pi.y;
+                    ri.x = ri.x - alpha * si.x; ri.y = ri.y - alpha * si.y;
+                    p2[i] = pi; s2[i] = si; v2[i] = vi; r2[i] = ri;
+                    a1 += ri.x * ri.x + ri.y * ri.y;
+                }
+            } else if (a.op == 11) {
+                spmv(P.At, P.r, epi_plain(P.t), sm, S, a0, a1);
+            } else if (a.op == 12) {
+                Epi e = epi_plain(P.w); e.dotv = P.r;
+                spmv(P.A, P.t, e, sm, S, a0, a1);
+            } else if (a.op == 13 && P.has_M) {
+                Epi e = epi_plain(P.w); e.dotv = P.r;
+                spmv(P.M, P.r, e, sm, S, a0, a1);
+            }
+            grid_sync(S);
+        }
+        if (a0 + a1 == 1.2345e-300) st.orth = a0;      // keep the sums alive
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.result->inner_iters = st.inner_iters;

@@ -70,6 +70,9 @@ PROTOTYPES = {
     "ipb_proj_create": (C.c_int, [_P, _P, C.c_double, C.c_int, C.c_double,
                                   C.c_int, C.POINTER(_P)]),
     "ipb_proj_refresh": (C.c_int, [_P, _P]),
+    "ipb_proj_set_aat_mode": (C.c_int, [_P, _P, C.c_int]),
+    "ipb_proj_aat_nnz": (_I64, [_P]),
+    "ipb_bench_phase": (C.c_int, [_P, _P, C.c_int, C.c_int, _D]),
     "ipb_proj_destroy": (C.c_int, [_P, _P]),
     "ipb_proj_null_space": (C.c_int, [_P, _P, _D, _D, C.POINTER(ProjInfo)]),
     "ipb_proj_least_squares": (C.c_int, [_P, _P, _D, _D, C.POINTER(ProjInfo)]),

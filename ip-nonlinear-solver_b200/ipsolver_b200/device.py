@@ -208,21 +208,33 @@ class DeviceProjector:
     device.  Holds the device copy of A (and A')."""
 
     def __init__(self, ctx, A, orth_tol=1e-12, max_refin=3, inner_rtol=1e-13,
-                 inner_maxit=1000):
+                 inner_maxit=1000, aat_mode=0):
         self.ctx = ctx
         self.A = A if isinstance(A, DeviceCSR) else DeviceCSR(ctx, A, True)
         self.m, self.n = self.A.shape
         self.params = (float(orth_tol), int(max_refin), float(inner_rtol),
-                       int(inner_maxit))
+                       int(inner_maxit), int(aat_mode))
         h = C.c_void_p()
-        ctx.check(ctx.lib.ipb_proj_create(ctx.h, self.A.h, *self.params, C.byref(h)))
+        ctx.check(ctx.lib.ipb_proj_create(ctx.h, self.A.h, *self.params[:4], C.byref(h)))
         self.h = h
         weakref.finalize(self, ctx.lib.ipb_proj_destroy, ctx.h, h)
+        if aat_mode:
+            self.set_aat_mode(aat_mode)
         self.last_info = None
         self.totals = dict(inner_iters=0, n_solves=0, n_refinements=0, applies=0)
 
     def refresh(self):
         self.ctx.check(self.ctx.lib.ipb_proj_refresh(self.ctx.h, self.h))
+
+    def set_aat_mode(self, mode):
+        """0: explicit A A' when it moves fewer bytes (default), 1: always
+        A then A', 2: always the explicit product."""
+        self.ctx.check(self.ctx.lib.ipb_proj_set_aat_mode(self.ctx.h, self.h, int(mode)))
+
+    @property
+    def aat_nnz(self):
+        """nnz of the explicit A A' held in HBM, or -1 when it is not held."""
+        return int(self.ctx.lib.ipb_proj_aat_nnz(self.h))
 
     def _note(self, info):
         self.last_info = info
@@ -331,6 +343,13 @@ def bench_inner_iterations(proj, x, iters):
     ms = C.c_double()
     proj.ctx.check(proj.ctx.lib.ipb_bench_inner_iterations(
         proj.ctx.h, proj.h, x.h, int(iters), C.byref(ms)))
+    return ms.value
+
+
+def bench_phase(proj, phase, reps):
+    ms = C.c_double()
+    proj.ctx.check(proj.ctx.lib.ipb_bench_phase(
+        proj.ctx.h, proj.h, int(phase), int(reps), C.byref(ms)))
     return ms.value
 
 

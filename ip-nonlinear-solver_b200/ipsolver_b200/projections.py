@@ -21,7 +21,10 @@ DENSE_METHODS = ("QRFactorization", "SVDFactorization")
 
 # knobs of the inner solve; ``options['inner_rtol']`` etc. reach here through
 # ``set_inner_options`` (they ride next to the reference's own option keys).
-_INNER = {"inner_rtol": 1e-13, "inner_maxit": 1000}
+# ``aat_mode``: 0 keep the explicit product A A' in HBM when that moves fewer
+# bytes per inner iteration (default), 1 always apply A' then A, 2 always
+# use the explicit product.
+_INNER = {"inner_rtol": 1e-13, "inner_maxit": 1000, "aat_mode": 0}
 
 
 def set_inner_options(**kw):
@@ -100,7 +103,7 @@ def _binding_for(A, orth_tol, max_refin):
     key = (A.shape, A.nnz)
     cached = ctx._pattern_cache.get(key)
     params = (float(orth_tol), int(max_refin), float(_INNER["inner_rtol"]),
-              int(_INNER["inner_maxit"]))
+              int(_INNER["inner_maxit"]), int(_INNER["aat_mode"]))
     if cached is not None and cached.params == params and cached.A.same_pattern(A):
         cached.A.update_values(A.data)
         cached.refresh()

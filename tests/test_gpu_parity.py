@@ -20,9 +20,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-8
 
 
-@pytest.fixture(scope="module")
-def dev():
+# every test runs with both representations of (A A') in the inner CG:
+# A then A' (two SpMVs) and the explicit product M = A A' (one SpMV)
+@pytest.fixture(scope="module", params=[1, 2], ids=["AtA", "explicitM"])
+def dev(request):
     from ipsolver_b200 import device, projections, qp_subproblem
+    projections.set_inner_options(aat_mode=request.param)
 
     class NS:
         pass
@@ -32,7 +35,8 @@ def dev():
     ns.projections = projections.projections
     ns.orthogonality = projections.orthogonality
     ns.qp = qp_subproblem
-    return ns
+    yield ns
+    projections.set_inner_options(aat_mode=0)
 
 
 @pytest.fixture(scope="module")
