@@ -106,6 +106,9 @@ struct ipb_ctx {
     } while (0)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+// stride of the sub-vectors carved out of one allocation: keeps every one of
+// them 256-byte aligned (TMA bulk copies need 16) with slack behind it
+static inline size_t vstride(int64_t len) { return ((size_t)len + PAD + 31) & ~(size_t)31; }
 
 template <typename T>
 static int dalloc(ipb_ctx *ctx, T **p, size_t count) {
@@ -145,7 +148,8 @@ static CsrView csr_view_t(const ipb_csr *m, const double *val_override = nullptr
 // Cut the rows of a CSR matrix into blocks of at most CHUNK nnz and RMAX rows
 // (greedy, in row order); a row longer than CHUNK becomes a block of its own.
 // rowptr is read back from the device (once per sparsity pattern).
-static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, int rows, int4 **d_desc, int *nblk);
+static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, const int *d_col, int rows,
+                        int4 **d_desc, int *nblk);
 
 // number of CTAs for a launch working on ``work`` items: enough to fill the
 // machine for large problems, a handful for tiny ones (cheap barriers).
@@ -154,7 +158,8 @@ static int grid_for(const ipb_ctx *ctx, int64_t work) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(ctx->blocks, want));
 }
 
-static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, int rows, int4 **d_desc, int *nblk) {
+static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, const int *d_col, int rows,
+                        int4 **d_desc, int *nblk) {
     std::vector<int> rp((size_t)rows + 1);
     CU(ctx, cudaMemcpyAsync(rp.data(), d_rowptr, ((size_t)rows + 1) * sizeof(int),
                             cudaMemcpyDeviceToHost, ctx->stream));
@@ -173,13 +178,17 @@ static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, int rows, int4 **d_de
             r1 = std::max(r1, hi);
         }
         desc.push_back(make_int4(r0, r1, base, rp[r1] - base));
+        desc.push_back(make_int4(0, 0, 0, 0));      // {c0, xcnt}: filled on the device
         r0 = r1;
     }
-    *nblk = (int)desc.size();
+    *nblk = (int)(desc.size() / 2);
     CHECK(dalloc(ctx, d_desc, desc.size()));
-    if (!desc.empty())
+    if (!desc.empty()) {
         CU(ctx, cudaMemcpyAsync(*d_desc, desc.data(), desc.size() * sizeof(int4),
                                 cudaMemcpyHostToDevice, ctx->stream));
+        k_block_colrange<<<cdiv((int64_t)*nblk * 32, 256), 256, 0, ctx->stream>>>(*nblk, *d_desc, d_col);
+        ctx->launches += 1;
+    }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     return IPB_OK;
 }
@@ -329,7 +338,7 @@ extern "C" int ipb_vec_create(ipb_ctx *ctx, int64_t len, ipb_vec **out) {
     if (!ctx || !out || len < 0) return IPB_ERR_INVALID;
     ipb_vec *v = new ipb_vec();
     v->len = len;
-    int s = dalloc(ctx, &v->d, (size_t)len);
+    int s = dalloc(ctx, &v->d, (size_t)len + PAD);      // slack: bulk copies round sizes up
     if (s != IPB_OK) { delete v; return s; }
     *out = v;
     return IPB_OK;
@@ -395,7 +404,7 @@ static int build_transpose(ipb_ctx *ctx, ipb_csr *m) {
                                               m->cols + 1, ctx->stream));
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CHECK(build_blocks(ctx, m->t_rowptr, m->cols, &m->t_desc, &m->t_nblk));
+    CHECK(build_blocks(ctx, m->t_rowptr, m->t_col, m->cols, &m->t_desc, &m->t_nblk));
     m->has_t = true;
     return IPB_OK;
 }
@@ -436,7 +445,7 @@ extern "C" int ipb_csr_create(ipb_ctx *ctx, int64_t rows, int64_t cols, int64_t 
     if (nnz) CU(ctx, cudaMemcpyAsync(m->val, data, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (rows == 0) CU(ctx, cudaMemsetAsync(m->rowptr, 0, sizeof(int), ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if ((s = build_blocks(ctx, m->rowptr, m->rows, &m->desc, &m->nblk)) != IPB_OK) return s;
+    if ((s = build_blocks(ctx, m->rowptr, m->col, m->rows, &m->desc, &m->nblk)) != IPB_OK) return s;
     if (with_transpose) {
         s = build_transpose(ctx, m);
         if (s != IPB_OK) return s;
@@ -477,8 +486,8 @@ static int run_matvec(ipb_ctx *ctx, const CsrView &M, const double *dx, double *
 
 static int host_in_out(ipb_ctx *ctx, int64_t nin, int64_t nout, const double *hin,
                        double **din, double **dout) {
-    CHECK(ensure_stage(ctx, (size_t)(nin + nout)));
-    *din = ctx->stage; *dout = ctx->stage + nin;
+    CHECK(ensure_stage(ctx, vstride(nin) + vstride(nout)));
+    *din = ctx->stage; *dout = ctx->stage + vstride(nin);
     if (nin) CU(ctx, cudaMemcpyAsync(*din, hin, (size_t)nin * 8, cudaMemcpyHostToDevice, ctx->stream));
     return IPB_OK;
 }
@@ -689,7 +698,7 @@ static int build_aat_pattern(ipb_ctx *ctx, ipb_proj *p) {
             cudaError_t e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); status = IPB_ERR_CUDA; }
             if (status == IPB_OK)
-                status = build_blocks(ctx, p->m_rowptr, m, &p->m_desc, &p->m_nblk);
+                status = build_blocks(ctx, p->m_rowptr, p->m_col, m, &p->m_desc, &p->m_nblk);
             if (status == IPB_OK) p->has_M = true;
         }
         if (status != IPB_OK) free_aat(p);
@@ -738,9 +747,10 @@ extern "C" int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int ma
     CHECK(dalloc(ctx, &p->nt_val, nnz + PAD));
     CHECK(dalloc(ctx, &p->dscale, m));
     CHECK(dalloc(ctx, &p->dnorm2, m));
-    CHECK(dalloc(ctx, &p->v, m)); CHECK(dalloc(ctx, &p->r, m)); CHECK(dalloc(ctx, &p->w, m));
-    CHECK(dalloc(ctx, &p->p, m)); CHECK(dalloc(ctx, &p->s, m)); CHECK(dalloc(ctx, &p->rhs, m));
-    CHECK(dalloc(ctx, &p->t, n));
+    CHECK(dalloc(ctx, &p->v, m + PAD)); CHECK(dalloc(ctx, &p->r, m + PAD));
+    CHECK(dalloc(ctx, &p->w, m + PAD)); CHECK(dalloc(ctx, &p->p, m + PAD));
+    CHECK(dalloc(ctx, &p->s, m + PAD)); CHECK(dalloc(ctx, &p->rhs, m + PAD));
+    CHECK(dalloc(ctx, &p->t, n + PAD));
     const char *env = getenv("IPB_EXPLICIT_AAT");      // 0 auto, 1 never, 2 always
     if (env) p->aat_mode = atoi(env);
     CHECK(build_aat_pattern(ctx, p));
@@ -895,7 +905,8 @@ static int run_pcg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, const double *d
     const int64_t n = P->A->cols, m = P->A->rows;
     if (H->n != n) IPB_FAIL(ctx, IPB_ERR_INVALID, "H is %lld x %lld but A has %lld columns",
                             (long long)H->n, (long long)H->n, (long long)n);
-    CHECK(ensure_ws(ctx, (size_t)7 * n));
+    const size_t ns = vstride(n);
+    CHECK(ensure_ws(ctx, 7 * ns));
     PcgArgs a;
     memset(&a, 0, sizeof a);
     a.H = hess_view(H); a.P = proj_view(P); a.S = sync_view(ctx);
@@ -905,8 +916,8 @@ static int run_pcg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, const double *d
     a.radius = radius; a.tol = tol;
     a.max_iter = max_iter; a.max_infeasible = max_inf;
     double *w = ctx->ws;
-    a.x = w; a.xn = w + n; a.r = w + 2 * n; a.p = w + 3 * n; a.Hp = w + 4 * n;
-    a.xfeas = w + 5 * n; a.tmp = w + 6 * n;
+    a.x = w; a.xn = w + ns; a.r = w + 2 * ns; a.p = w + 3 * ns; a.Hp = w + 4 * ns;
+    a.xfeas = w + 5 * ns; a.tmp = w + 6 * ns;
     a.allvecs = d_allvecs; a.allvecs_cap = allvecs_cap;
     a.result = (PcgArgs::Result *)ctx->d_result;
     float ms = 0.f;
@@ -958,10 +969,11 @@ extern "C" int ipb_projected_cg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, co
     const int64_t n = P->A->cols, m = P->A->rows;
     const bool box = lb && ub;
     if (!allvecs) allvecs_cap = 0;
-    size_t need = (size_t)n * (2 + (box ? 2 : 0)) + (size_t)m + (size_t)allvecs_cap * n;
+    const size_t ns = vstride(n), ms = vstride(m);
+    size_t need = ns * (2 + (box ? 2 : 0)) + ms + (size_t)allvecs_cap * n;
     CHECK(ensure_stage(ctx, need));
-    double *dc = ctx->stage, *db = dc + n, *dx = db + m, *dlb = dx + n, *dub = dlb + (box ? n : 0);
-    double *dall = allvecs_cap ? dub + (box ? n : 0) : nullptr;
+    double *dc = ctx->stage, *db = dc + ns, *dx = db + ms, *dlb = dx + ns, *dub = dlb + (box ? ns : 0);
+    double *dall = allvecs_cap ? dub + (box ? ns : 0) : nullptr;
     if (n) CU(ctx, cudaMemcpyAsync(dc, c, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (m) CU(ctx, cudaMemcpyAsync(db, b, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (box && n) {
@@ -988,9 +1000,10 @@ extern "C" int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b, d
     if (!ctx || !P || !b || !x) return IPB_ERR_INVALID;
     const int64_t n = P->A->cols, m = P->A->rows;
     const bool box = lb && ub;
-    CHECK(ensure_stage(ctx, (size_t)m + (box ? 2 * n : 0)));
-    CHECK(ensure_ws(ctx, (size_t)7 * n + m));
-    double *db = ctx->stage, *dlb = db + m, *dub = dlb + (box ? n : 0);
+    const size_t ns = vstride(n), mstr = vstride(m);
+    CHECK(ensure_stage(ctx, mstr + (box ? 2 * ns : 0)));
+    CHECK(ensure_ws(ctx, 7 * ns + mstr));
+    double *db = ctx->stage, *dlb = db + mstr, *dub = dlb + (box ? ns : 0);
     if (m) CU(ctx, cudaMemcpyAsync(db, b, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (box && n) {
         CU(ctx, cudaMemcpyAsync(dlb, lb, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1003,8 +1016,8 @@ extern "C" int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b, d
     a.n = (int)n; a.m = (int)m; a.b = db; a.lb = box ? dlb : nullptr; a.ub = box ? dub : nullptr;
     a.has_box = box; a.radius = trust_radius;
     double *w = ctx->ws;
-    a.newton = w; a.cauchy = w + n; a.g = w + 2 * n; a.x1 = w + 3 * n; a.x2 = w + 4 * n;
-    a.out = w + 5 * n; a.mtmp = w + 7 * n;
+    a.newton = w; a.cauchy = w + ns; a.g = w + 2 * ns; a.x1 = w + 3 * ns; a.x2 = w + 4 * ns;
+    a.out = w + 5 * ns; a.mtmp = w + 7 * ns;
     a.result = (ProjArgs::Result *)ctx->d_result;
     float ms = 0.f;
     CHECK(launch_coop(ctx, k_dogleg, a, proj_grid(ctx, P), &ms));

@@ -26,12 +26,32 @@ namespace ipb {
 
 constexpr int THREADS = 256;          // threads per CTA of every kernel
 constexpr int WARPS = THREADS / 32;
-constexpr int CHUNK = 2048;           // nnz staged per pipeline stage
-constexpr int RMAX = 1536;            // max rows of one row block
+#ifndef IPB_CHUNK
+#define IPB_CHUNK 2048
+#endif
+#ifndef IPB_RMAX
+#define IPB_RMAX 512
+#endif
+#ifndef IPB_NSTAGE
+#define IPB_NSTAGE 2
+#endif
+#ifndef IPB_MIN_BLOCKS
+#define IPB_MIN_BLOCKS 3
+#endif
+#ifndef IPB_XMAX
+#define IPB_XMAX 1152
+#endif
+constexpr int XMAX = IPB_XMAX;        // doubles of the x slice staged with a block
+constexpr int CHUNK = IPB_CHUNK;      // nnz staged per pipeline stage
+constexpr int RMAX = IPB_RMAX;        // max rows of one row block
+constexpr int NSTAGE = IPB_NSTAGE;    // pipeline stages per CTA
+constexpr int NPT = CHUNK / THREADS;  // products per thread and block
+constexpr int RPT = RMAX / THREADS;   // rows per thread and block
 constexpr int PAD = 8;                // over-read slack of the bulk copies (elements)
-constexpr int MIN_BLOCKS = 3;         // CTAs per SM the kernels are compiled for
+constexpr int MIN_BLOCKS = IPB_MIN_BLOCKS;   // CTAs per SM the kernels are compiled for
 constexpr int NSLOT = 8;              // reduction slots per barrier
 constexpr int MAX_GRID = 2048;        // upper bound on CTAs of a launch
+static_assert(CHUNK % THREADS == 0 && RMAX % THREADS == 0 && NSTAGE >= 2, "block shape");
 
 enum { OP_SUM = 0, OP_MIN = 1, OP_MAX = 2 };
 
@@ -39,7 +59,7 @@ enum { OP_SUM = 0, OP_MIN = 1, OP_MAX = 2 };
 struct CsrView {
     int rows, cols;
     int nblk;                 // row blocks (built at upload, <= CHUNK nnz each)
-    const int4 *desc;         // per block {r0, r1, p0, len}
+    const int4 *desc;         // per block {r0, r1, p0, len}, {c0, xcnt, -, -}
     const int *rowptr;
     const int *col;
     const double *val;
@@ -96,6 +116,9 @@ __device__ __forceinline__ int ldg_stream(const int *p) { return __ldg(p); }
 // cross-GPU exchange can ride on it.  Requires all CTAs co-resident
 // (cudaLaunchCooperativeKernel).
 __device__ __forceinline__ void grid_sync(const SyncView &S) {
+    // vectors written in this phase are read by TMA bulk copies (async proxy)
+    // in the next one: order this thread's generic-proxy writes before them
+    asm volatile("fence.proxy.async.global;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned nb = 1;
@@ -168,18 +191,22 @@ __device__ __forceinline__ void collect(const SyncView &S, int nslots,
 // ---------------------------------------------------------------- shared memory
 // One pipeline stage = the val / col / rowptr slices of one row block, landed
 // by three 1-D TMA bulk copies (cp.async.bulk) that complete on the stage's
-// mbarrier.  Two stages: the copy of the CTA's next row block is in flight
-// while the current one is multiplied, summed and written out.
+// ``full`` mbarrier.  NSTAGE stages per CTA; a warp that has finished a block
+// bumps the stage's ``done`` counter and the last one to do so refills the
+// stage with the block NSTAGE further on -- the warps of a CTA run decoupled
+// (no __syncthreads in the block loop) and NSTAGE - 1 copies stay in flight.
 struct __align__(128) Stage {
-    double val[CHUNK + PAD];      // products overwrite the values in place
+    double val[CHUNK + PAD];
+    double xs[XMAX];              // x[c0 .. c0 + xcnt) of the block, when it fits
     int col[CHUNK + PAD];
     int rowptr[RMAX + PAD];
 };
 
 struct __align__(128) Smem {
-    Stage st[2];
-    unsigned long long mbar[2];
-    unsigned uses[2];             // completed uses of each stage (phase parity)
+    Stage st[NSTAGE];
+    unsigned long long full[NSTAGE];
+    unsigned done[NSTAGE];        // warps that have finished with the stage's block
+    unsigned seq;                 // stage uses of this CTA so far (slot = seq % NSTAGE)
     double red[WARPS];
     double out[NSLOT];
     int ops[NSLOT];
@@ -191,9 +218,12 @@ __device__ __forceinline__ unsigned smem_addr(const void *p) {
 
 __device__ __forceinline__ void pipeline_init(Smem &sm) {
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.mbar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.mbar[1])));
-        sm.uses[0] = 0; sm.uses[1] = 0;
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.full[s])));
+            sm.done[s] = 0;
+        }
+        sm.seq = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -206,18 +236,25 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
         ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(mbar)) : "memory");
 }
 
+__device__ __forceinline__ bool mbar_try(unsigned long long *mbar, unsigned parity) {
+    unsigned done;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done) : "r"(smem_addr(mbar)), "r"(parity) : "memory");
+    return done != 0;
+}
+
 __device__ __forceinline__ void mbar_wait(unsigned long long *mbar, unsigned parity,
                                           int *abort_flag) {
-    unsigned done = 0;
     long long spins = 0;
-    while (!done) {
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(done) : "r"(smem_addr(mbar)), "r"(parity) : "memory");
+    while (!mbar_try(mbar, parity))
         if (++spins > (1ll << 26)) { *abort_flag = 2; __trap(); }
-    }
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(mbar)) : "memory");
 }
 
 // ---------------------------------------------------------------- SpMV
@@ -239,93 +276,140 @@ __device__ __forceinline__ Epi epi_plain(double *y) {
     e.wv = nullptr; e.post = nullptr; e.want_sq = 0; e.accumulate = 0; return e;
 }
 
-__device__ __forceinline__ void row_out(const Epi &e, int r, double s,
-                                        double &acc0, double &acc1) {
+// addv[r] and dotv[r] are passed in (fetched together with the gathers, so
+// their latency overlaps); the rarely used operands are read here.
+__device__ __forceinline__ void row_out(const Epi &e, int r, double s, double addv_r,
+                                        double dotv_r, double &acc0, double &acc1) {
     double y = s;
     if (e.sa != 1.0) y = e.sa * y;
-    if (e.addv) y = y + e.sb * e.addv[r];
+    if (e.addv) y = y + e.sb * addv_r;
     if (e.accumulate) y = e.y[r] + y;
-    if (e.dotv) acc0 += y * e.dotv[r];
+    if (e.dotv) acc0 += y * dotv_r;
     if (e.want_sq) acc1 += (e.wv ? e.wv[r] * (y * y) : y * y);
     e.y[r] = e.post ? y * e.post[r] : y;
 }
 
-// Row block descriptor {r0, r1, p0, len}: rows [r0, r1), nnz [p0, p0 + len).
+// Row block descriptor: {r0, r1, p0, len} rows [r0, r1), nnz [p0, p0 + len);
+// {c0, xcnt}: the block's columns lie in [c0, c0 + xcnt) (c0, xcnt even) and
+// xcnt <= XMAX, or xcnt = 0 when the column span is too wide to stage.
 // Blocks are cut at upload so that len <= CHUNK and r1 - r0 <= RMAX; a row
 // longer than CHUNK is a block of its own (len > CHUNK).
+struct BlockDesc { int r0, r1, p0, len, c0, xcnt; };
 
-// Thread 0 starts the three bulk copies of a row block into stage ``s``.
+__device__ __forceinline__ BlockDesc load_desc(const int4 *desc, size_t blk) {
+    const int4 a = __ldg(desc + 2 * blk), b = __ldg(desc + 2 * blk + 1);
+    BlockDesc d; d.r0 = a.x; d.r1 = a.y; d.p0 = a.z; d.len = a.w; d.c0 = b.x; d.xcnt = b.y;
+    return d;
+}
+
+// The calling thread starts the bulk copies of a row block into stage ``s``: the val /
+// col / rowptr slices and, when xstage, the slice of x the block's columns
+// address -- so the block is then processed entirely out of shared memory.
 // Sources are aligned down to 4 elements (16 B for ints, 32 B for doubles)
-// and sizes rounded up to 4; the arrays are allocated with PAD slack.
-__device__ __forceinline__ void stage_issue(const CsrView &M, const int4 d,
+// and sizes rounded up to 4; the arrays are allocated with PAD slack.  A
+// long-row block does not use its stage: a plain arrive completes the phase
+// so that the parity of every slot keeps advancing once per use.
+__device__ __forceinline__ void stage_issue(const CsrView &M, const BlockDesc d,
+                                            const double *x, bool xstage,
                                             Smem &sm, int s) {
-    if (threadIdx.x == 0 && d.w <= CHUNK) {
-        const int p0a = d.z & ~3, r0a = d.x & ~3;
-        const unsigned cnt = (unsigned)((d.z + d.w - p0a + 3) & ~3);
-        const unsigned rcnt = (unsigned)((d.y - r0a + 1 + 3) & ~3);
+    if (d.len <= CHUNK) {
+        const int p0a = d.p0 & ~3, r0a = d.r0 & ~3;
+        const unsigned cnt = (unsigned)((d.p0 + d.len - p0a + 3) & ~3);
+        const unsigned rcnt = (unsigned)((d.r1 - r0a + 1 + 3) & ~3);
+        const unsigned xcnt = xstage ? (unsigned)d.xcnt : 0u;
         Stage &st = sm.st[s];
-        // the stage was last written by ordinary stores (products in place):
-        // order them before the async-proxy writes of the new copy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        unsigned tx = cnt * 12u + rcnt * 4u;
+        // the stage was last read through the generic proxy, and x was written
+        // through it: order both before the async-proxy copies
+        asm volatile("fence.proxy.async;" ::: "memory");
+        unsigned tx = cnt * 12u + rcnt * 4u + xcnt * 8u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                     ::"r"(smem_addr(&sm.mbar[s])), "r"(tx) : "memory");
-        bulk_g2s(st.val, M.val + p0a, cnt * 8u, &sm.mbar[s]);
-        bulk_g2s(st.col, M.col + p0a, cnt * 4u, &sm.mbar[s]);
-        bulk_g2s(st.rowptr, M.rowptr + r0a, rcnt * 4u, &sm.mbar[s]);
+                     ::"r"(smem_addr(&sm.full[s])), "r"(tx) : "memory");
+        bulk_g2s(st.val, M.val + p0a, cnt * 8u, &sm.full[s]);
+        bulk_g2s(st.col, M.col + p0a, cnt * 4u, &sm.full[s]);
+        bulk_g2s(st.rowptr, M.rowptr + r0a, rcnt * 4u, &sm.full[s]);
+        if (xcnt) bulk_g2s(st.xs, x + d.c0, xcnt * 8u, &sm.full[s]);
+    } else {
+        mbar_arrive(&sm.full[s]);
     }
 }
 
-// y = M x over all row blocks of M (grid-stride), double-buffered: while a
-// block is processed the TMA copy of the CTA's next block is in flight and
-// the descriptor of the one after that is being fetched.
-__device__ __noinline__ void spmv(const CsrView M, const double *x, const Epi e,
-                                  Smem &sm, const SyncView &S, double &acc0,
-                                  double &acc1) {
+// Rows of one staged block, one thread per row, single pass.  XS: x comes
+// from the staged slice (shared memory) instead of global gathers.  FAST:
+// the epilogue is y = sum (plus the optional dot with dotv), the form of the
+// two products inside the CG loops.  Entries are added in index order -- the
+// left-to-right order of scipy's csr_matvec, so with -fmad=false row sums are
+// bit-identical to it.
+template <bool XS, bool FAST>
+__device__ __forceinline__ void block_rows(const Stage &st, const BlockDesc &d,
+                                           const double *x, const Epi &e,
+                                           double &acc0, double &acc1) {
+    const int p0a = d.p0 & ~3, r0a = d.r0 & ~3;
+    const double *sv = st.val - p0a;          // sv[q], q a global nnz index
+    const int *sc = st.col - p0a;
+    const int *rp = st.rowptr - r0a;          // rp[r], r a global row index
+    const double *xv = XS ? (st.xs - d.c0) : x;   // xv[c], c a global column index
+    const bool dot_is_x = XS && (e.dotv == x);
+    for (int r = d.r0 + (int)threadIdx.x; r < d.r1; r += THREADS) {
+        int q = rp[r];
+        const int qe = rp[r + 1];
+        double dvv = 0.0, avv = 0.0;
+        if (e.dotv) {
+            const unsigned off = (unsigned)(r - d.c0);
+            dvv = (dot_is_x && off < (unsigned)d.xcnt) ? st.xs[off] : e.dotv[r];
+        }
+        if (!FAST && e.addv) avv = e.addv[r];
+        double sum = 0.0;
+        for (; q + 1 < qe; q += 2) {
+            const int c0 = sc[q], c1 = sc[q + 1];
+            const double v0 = sv[q], v1 = sv[q + 1];
+            const double x0 = xv[c0], x1 = xv[c1];
+            sum += v0 * x0;
+            sum += v1 * x1;
+        }
+        if (q < qe) sum += sv[q] * xv[sc[q]];
+        if (FAST) {
+            if (e.dotv) acc0 += sum * dvv;
+            e.y[r] = sum;
+        } else {
+            row_out(e, r, sum, avv, dvv, acc0, acc1);
+        }
+    }
+}
+
+// y = M x over the row blocks of M; CTA b takes the contiguous block range
+// [b*per, (b+1)*per).  Thread 0 starts the first NSTAGE copies; after that a
+// stage is refilled by the last warp that finishes with it.
+template <bool FAST>
+__device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const Epi e,
+                                       Smem &sm, const SyncView &S, double &acc0,
+                                       double &acc1) {
     const int tid = threadIdx.x;
-    const int G = gridDim.x;
-    int blk = blockIdx.x;
-    if (blk >= M.nblk) return;
-    int4 cur = __ldg(M.desc + blk);
-    int4 nxt = (blk + G < M.nblk) ? __ldg(M.desc + blk + G) : cur;
-    int s = 0;
-    stage_issue(M, cur, sm, s);
-    for (; blk < M.nblk; blk += G) {
-        int4 nn = (blk + 2 * G < M.nblk) ? __ldg(M.desc + blk + 2 * G) : nxt;
-        if (blk + G < M.nblk) stage_issue(M, nxt, sm, s ^ 1);
-        const int r0 = cur.x, r1 = cur.y, p0 = cur.z, len = cur.w;
-        if (len <= CHUNK) {
-            Stage &st = sm.st[s];
-            mbar_wait(&sm.mbar[s], sm.uses[s] & 1u, S.abort_flag);
-            const int p0a = p0 & ~3, r0a = r0 & ~3;
-            double *pv = st.val + (p0 - p0a);
-            const int *pc = st.col + (p0 - p0a);
-            int k = tid;
-            for (; k + 3 * THREADS < len; k += 4 * THREADS) {
-                int c0 = pc[k], c1 = pc[k + THREADS];
-                int c2 = pc[k + 2 * THREADS], c3 = pc[k + 3 * THREADS];
-                double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
-                pv[k] = pv[k] * x0;
-                pv[k + THREADS] = pv[k + THREADS] * x1;
-                pv[k + 2 * THREADS] = pv[k + 2 * THREADS] * x2;
-                pv[k + 3 * THREADS] = pv[k + 3 * THREADS] * x3;
-            }
-            for (; k < len; k += THREADS) pv[k] = pv[k] * x[pc[k]];
-            __syncthreads();
-            if (tid == 0) sm.uses[s] += 1;
-            const double *prod = st.val - p0a;        // prod[q], q a global nnz index
-            const int *rp = st.rowptr - r0a;          // rp[r], r a global row index
-            for (int r = r0 + tid; r < r1; r += THREADS) {
-                int rs = rp[r], re = rp[r + 1];
-                double sum = 0.0;
-                for (int q = rs; q < re; ++q) sum += prod[q];
-                row_out(e, r, sum, acc0, acc1);
-            }
-            __syncthreads();
+    __syncthreads();                       // sm.seq of the previous call is visible
+    const int per = (M.nblk + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int first = (int)blockIdx.x * per;
+    const int nmine = min(per, M.nblk - first);
+    if (nmine <= 0) return;
+    const unsigned base = sm.seq;
+    const int4 *dp = M.desc + 2 * (size_t)first;
+    // x slices are staged only when the bulk-copy source is 16-byte aligned
+    const bool xstage = (reinterpret_cast<size_t>(x) & 15) == 0;
+    if (tid == 0)
+        for (int k = 0; k < NSTAGE && k < nmine; ++k)
+            stage_issue(M, load_desc(dp, k), x, xstage, sm, (base + k) % NSTAGE);
+    BlockDesc d = load_desc(dp, 0);
+    for (int j = 0; j < nmine; ++j) {
+        const BlockDesc dnext = load_desc(dp, min(j + 1, nmine - 1));
+        const BlockDesc dfar = load_desc(dp, min(j + NSTAGE, nmine - 1));
+        const unsigned u = base + j;
+        const int s = u % NSTAGE;
+        if (d.len <= CHUNK) {
+            mbar_wait(&sm.full[s], (u / NSTAGE) & 1u, S.abort_flag);
+            if (xstage && d.xcnt > 0) block_rows<true, FAST>(sm.st[s], d, x, e, acc0, acc1);
+            else block_rows<false, FAST>(sm.st[s], d, x, e, acc0, acc1);
         } else {
             // one long row: the whole CTA strides over it, fixed-order tree
             double part = 0.0;
-            for (int q = p0 + tid; q < p0 + len; q += THREADS)
+            for (int q = d.p0 + tid; q < d.p0 + d.len; q += THREADS)
                 part += ldg_stream(M.val + q) * x[ldg_stream(M.col + q)];
             part = warp_reduce(part, OP_SUM);
             __syncthreads();
@@ -335,14 +419,34 @@ __device__ __noinline__ void spmv(const CsrView M, const double *x, const Epi e,
                 double sum = sm.red[0];
 #pragma unroll
                 for (int w = 1; w < WARPS; ++w) sum += sm.red[w];
-                row_out(e, r0, sum, acc0, acc1);
+                row_out(e, d.r0, sum, e.addv ? e.addv[d.r0] : 0.0,
+                        e.dotv ? e.dotv[d.r0] : 0.0, acc0, acc1);
             }
-            __syncthreads();
         }
-        cur = nxt;
-        nxt = nn;
-        s ^= 1;
+        // hand the stage back; the last warp to do so refills it
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            __threadfence_block();
+            const unsigned old = atomicAdd(&sm.done[s], 1u);
+            if (old == WARPS - 1) {
+                atomicExch(&sm.done[s], 0u);
+                __threadfence_block();
+                if (j + NSTAGE < nmine) stage_issue(M, dfar, x, xstage, sm, s);
+            }
+        }
+        d = dnext;
     }
+    __syncthreads();
+    if (tid == 0) sm.seq = base + (unsigned)nmine;
+}
+
+__device__ __forceinline__ void spmv(const CsrView M, const double *x, const Epi e,
+                                     Smem &sm, const SyncView &S, double &acc0,
+                                     double &acc1) {
+    const bool fast = !e.addv && e.sa == 1.0 && !e.accumulate && !e.want_sq &&
+                      !e.post && !e.wv;
+    if (fast) spmv_impl<true>(M, x, e, sm, S, acc0, acc1);
+    else spmv_impl<false>(M, x, e, sm, S, acc0, acc1);
 }
 
 // Dense row-major GEMV, one warp per row, same epilogue.
@@ -363,7 +467,8 @@ __device__ __noinline__ void gemv_dense(const double *D, int nx, const double *x
         }
         for (; c < nx; c += 32) s0 += ldg_stream(row + c) * x[c];
         double s = warp_reduce((s0 + s1) + (s2 + s3), OP_SUM);
-        if (lane == 0) row_out(e, r, s, acc0, acc1);
+        if (lane == 0)
+            row_out(e, r, s, e.addv ? e.addv[r] : 0.0, e.dotv ? e.dotv[r] : 0.0, acc0, acc1);
     }
 }
 
@@ -445,7 +550,7 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
                                         int fixed_iters = 0) {
     const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
     const int m = P.m;
-    double a0, a1;
+    double a0;
     // r = rhs, v = p = s = 0
     double gpart = 0.0;
     for (int i = gt; i < m; i += nt) {
@@ -1312,6 +1417,33 @@ __global__ void k_aat_values(int rows, const int *rowptr, const int *col,
             else ++q;
         }
         m_val[e] = s;
+    }
+}
+
+// column range of every row block -> {c0, xcnt} (second int4 of its descriptor)
+__global__ void k_block_colrange(int nblk, int4 *desc, const int *col) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nblk) return;
+    const int4 a = desc[2 * (size_t)warp];
+    int lo = 0x7fffffff, hi = -1;
+    if (a.w <= CHUNK)
+        for (int q = a.z + lane; q < a.z + a.w; q += 32) {
+            const int c = col[q];
+            lo = min(lo, c); hi = max(hi, c);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+        int c0 = 0, xcnt = 0;
+        if (hi >= lo) {
+            c0 = lo & ~1;
+            xcnt = (hi - c0 + 2) & ~1;
+            if (xcnt > XMAX) { c0 = 0; xcnt = 0; }
+        }
+        desc[2 * (size_t)warp + 1] = make_int4(c0, xcnt, 0, 0);
     }
 }
 

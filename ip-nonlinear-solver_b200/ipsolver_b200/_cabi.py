@@ -10,7 +10,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libipsolver_b200.so")
+# IPB_LIB_PATH selects another build of the same library (tuning variants
+# compiled with different block-shape constants, scripts/build_variants.sh)
+LIB_PATH = os.environ.get("IPB_LIB_PATH") or os.path.join(_HERE, "libipsolver_b200.so")
 
 IPB_OK = 0
 IPB_ERR_INVALID = 1
