@@ -44,20 +44,37 @@ METRIC = "projected_cg_iterations_per_s"
 UNIT = "it/s"
 
 
-def algorithmic_bytes(n, m, nnzH, nnzA, niter, inner_iters, n_z, n_refin, n_hp):
-    """Compulsory HBM bytes of one launch:
-    B_spmv = 12 nnz + 4 (rows+1) + 8 cols + 8 rows; inner CG iteration
-    B_in = B_A + B_At + 56 m; one Z apply = B_A + B_At + 8 n (+ its inner
-    iterations) + B_A for the orthogonality product, again per refinement;
-    outer iteration = B_H + 72 n (+ its Z apply)."""
+def algorithmic_bytes(n, m, nnzH, nnzA, nnzM, niter, inner_iters, n_z, n_refin, n_hp):
+    """Compulsory HBM bytes of one launch of the solve kernel, for the
+    algorithm AS RUN.  8-byte values, 4-byte indices,
+    every matrix / vector counted once per logical read or write:
+
+      B_spmv(rows, cols, nnz) = 12 nnz + 4 (rows+1) + 8 cols + 8 rows
+      inner CG iteration, explicit M = A A' (nnzM > 0):
+          B_in = B_spmv(m, m, nnzM) + 72 m     (one SpMV; fused update = 5 reads + 4 writes)
+      inner CG iteration, A then A' (nnzM < 0):
+          B_in = B_A + B_At + 8 m + 72 m       (two SpMVs, re-read of r for the dot)
+      one Z apply = 2 B_A + B_At + 8 n (+ its inner iterations), again per refinement
+      outer iteration = B_H + 72 n (+ its Z apply)
+
+    ``survey`` is the same launch priced with SURVEY.md section 8d's model
+    (B_in = B_A + B_At + 56 m: two SpMVs and an idealised 7-pass update),
+    i.e. the traffic the reference formulation would need."""
     B_H = 12 * nnzH + 4 * (n + 1) + 16 * n
     B_A = 12 * nnzA + 4 * (m + 1) + 8 * n + 8 * m
     B_At = 12 * nnzA + 4 * (n + 1) + 8 * m + 8 * n
-    B_in = B_A + B_At + 56 * m
-    total = inner_iters * B_in
-    total += (n_z + n_refin) * (2 * B_A + B_At + 8 * n)
-    total += n_hp * B_H + niter * 72 * n
-    return total, dict(B_H=B_H, B_A=B_A, B_At=B_At, B_in=B_in)
+    if nnzM > 0:
+        B_M = 12 * nnzM + 4 * (m + 1) + 16 * m
+        B_in = B_M + 72 * m
+    else:
+        B_M = None
+        B_in = B_A + B_At + 8 * m + 72 * m
+    B_in_survey = B_A + B_At + 56 * m
+    rest = (n_z + n_refin) * (2 * B_A + B_At + 8 * n) + n_hp * B_H + niter * 72 * n
+    total = inner_iters * B_in + rest
+    survey = inner_iters * B_in_survey + rest
+    return total, survey, dict(B_H=B_H, B_A=B_A, B_At=B_At, B_M=B_M, B_in=B_in,
+                               B_in_survey=B_in_survey)
 
 
 class ClockSampler:
@@ -192,7 +209,7 @@ def workload_config(args):
                            args.iters, args.inner_rtol),
             "n": args.n, "m": args.n // 2, "iters_per_step": args.iters,
             "pattern": args.pattern, "inner_rtol": args.inner_rtol,
-            "l2": "working set per inner iteration (~0.94 GB at n=1e7) exceeds "
+            "l2": "working set per inner iteration (~0.7 GB at n=1e7) exceeds "
                   "the 126 MB L2; no explicit flush",
             "parallelism": "1 GPU" if args.gpus == 1 else "row-partitioned x%d" % args.gpus}
 
@@ -255,8 +272,9 @@ def run_b200(args):
     i0 = infos[-1]
     has_b = 1
     n_z = int(i0.n_solves) - int(i0.n_refinements) - has_b
-    bytes_launch, parts = algorithmic_bytes(
-        n, m, H.nnz, A.nnz, int(i0.niter), int(i0.inner_iters), n_z,
+    nnzM = proj.aat_nnz
+    bytes_launch, bytes_survey, parts = algorithmic_bytes(
+        n, m, H.nnz, A.nnz, nnzM, int(i0.niter), int(i0.inner_iters), n_z,
         int(i0.n_refinements), int(i0.n_spmv_h))
     avg_ms = float(np.mean(kernel_ms))
     peak, peak_src = peaks()
@@ -273,10 +291,20 @@ def run_b200(args):
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_launch,
+                "bytes_model": "as run: inner CG on the explicit product M = A A' "
+                               "(nnzM = %d), B_in = B_M + 72 m" % nnzM if nnzM > 0 else
+                               "as run: inner CG applies A' then A, B_in = B_A + B_At + 80 m",
                 "avg_launch_ms": avg_ms,
                 "inner_iters_per_launch": int(i0.inner_iters),
                 "inner_iters_per_projection": int(i0.inner_iters) / max(int(i0.n_solves), 1),
-                "bytes_model": parts}
+                "bytes_per_unit": parts,
+                "survey_8d_model": {
+                    "algorithmic_bytes_per_launch": bytes_survey,
+                    "effective_GBs": bytes_survey / (avg_ms * 1e-3) / 1e9,
+                    "effective_frac": bytes_survey / (avg_ms * 1e-3) / 1e9 / peak,
+                    "note": "same launch priced with SURVEY.md 8d's two-SpMV formulation "
+                            "(B_in = B_A + B_At + 56 m); exceeds `achieved` because the "
+                            "explicit product moves fewer bytes per inner iteration"}}
 
     # inner CG iteration in isolation (same device code, fixed count)
     inner_ms = device.bench_inner_iterations(proj, dc, 50)

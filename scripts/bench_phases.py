@@ -31,7 +31,20 @@ phases = [
     ("w = A t, w.r", 2, B(A.nnz, m, n) + 8 * m),
     ("w = M r, w.r", 3, B(nnzM, m, m)),
     ("barrier only", 4, 0),
+    ("M r copy pipeline only", 5, 12 * nnzM + 4 * (m + 1) + 8 * m),
 ]
+import torch  # noqa: E402
+_a = torch.empty(1 << 27, dtype=torch.float64, device='cuda')
+_b = torch.empty_like(_a)
+_e0, _e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+_best = 1e9
+for _ in range(6):
+    _e0.record(); _b.copy_(_a); _e1.record(); torch.cuda.synchronize()
+    _best = min(_best, _e0.elapsed_time(_e1))
+print("copy bandwidth of this box, this process: %.0f GB/s (2 x 1 GiB / %.3f ms)" % (2 * _a.numel() * 8 / _best / 1e6, _best))
+del _a, _b
+import subprocess  # noqa: E402
+print(subprocess.run(['nvidia-smi', '--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu', '--format=csv,noheader'], capture_output=True, text=True).stdout.strip())
 print("n=%d m=%d nnzA=%d nnzM=%d grid=%s peak=%.0f GB/s" % (n, m, A.nnz, nnzM, ctx.grid(), PEAK))
 out = {}
 for name, ph, nbytes in phases:
