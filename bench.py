@@ -230,8 +230,7 @@ def run_b200(args):
     from ipsolver_b200.qp_subproblem import projected_cg, HessianOperator
 
     if args.gpus != 1:
-        raise SystemExit("multi-GPU row partition: see bench_multi (not in this round's "
-                         "first slice); run with --gpus 1")
+        return run_b200_dist(args)
     rank = 0
     n, m = args.n, args.n // 2
     set_inner_options(inner_rtol=args.inner_rtol)
@@ -363,6 +362,137 @@ def run_b200(args):
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+
+def run_b200_dist(args):
+    """N ranks (torchrun), the same QP row-partitioned over the GPUs of one
+    box: strong scaling.  Each rank runs the same persistent kernel on its
+    block; ghost entries and reductions cross NVLink inside the kernel
+    (peer-memory stores + flag barriers), torch.distributed is used for setup
+    and for the max-over-ranks clock only."""
+    import torch
+    import torch.distributed as dist
+    from ipsolver_b200 import synthetic, distributed as D
+
+    rank = int(os.environ.get("RANK", "0"))
+    size = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if size != args.gpus:
+        raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d)"
+                         % (args.gpus, args.gpus, size))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    gloo = dist.new_group(backend="gloo")
+    n, m = args.n, args.n // 2
+    t0 = time.perf_counter()
+    H, A, c, b = synthetic.make_qp(n, args.pattern, args.kappa, seed=0)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    S = D.DistSolver(H, A, rank, size, group=gloo, device=local, inner_rtol=args.inner_rtol)
+    t_setup = time.perf_counter() - t0
+    ctx = S.ctx
+    c_loc, b_loc = S.local(c, 0), S.local(b, 1)
+    dc, db = S.vector(c_loc), S.vector(b_loc, space=1)
+    dx = S.vector(space=0)
+
+    def sync_all():
+        ctx.sync()
+        dist.barrier()
+
+    for _ in range(args.warmup):
+        S.projected_cg(dc, db, dx, tol=1e-30, max_iter=args.iters)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    sync_all()
+    infos, kernel_ms = [], []
+    ctx.timer_start()
+    for _ in range(args.steps):
+        info = S.projected_cg(dc, db, dx, tol=1e-30, max_iter=args.iters)
+        infos.append(info)
+        kernel_ms.append(info.kernel_ms)
+    my_ms = ctx.timer_stop()
+    sync_all()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([my_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    niter = sum(int(i.niter) for i in infos)
+    value = niter / (total_ms * 1e-3)
+
+    # e2e: host blocks in pinned memory -> device, solve, result block back
+    hc = torch.from_numpy(c_loc).pin_memory().numpy()
+    hb = torch.from_numpy(b_loc).pin_memory().numpy()
+    hx = torch.empty(S.n_own, dtype=torch.float64).pin_memory().numpy()
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(args.steps):
+        dc.upload(hc)
+        db.upload(hb)
+        inf = S.projected_cg(dc, db, dx, tol=1e-30, max_iter=args.iters)
+        dx.download(hx)
+        e2e_iters += int(inf.niter)
+    ctx.sync()
+    t_my = time.perf_counter() - t0
+    t = torch.tensor([t_my], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_e2e = float(t.item())
+
+    # roofline of the solve kernel: whole-problem bytes over the max-over-ranks time
+    i0 = infos[-1]
+    nnzM = 0
+    nnzM_loc = torch.tensor([S.parts["M"].nnz], dtype=torch.int64, device="cuda")
+    dist.all_reduce(nnzM_loc)
+    nnzM = int(nnzM_loc.item())
+    n_z = int(i0.n_solves) - int(i0.n_refinements) - 1
+    bytes_launch, bytes_survey, parts = algorithmic_bytes(
+        n, m, H.nnz, A.nnz, nnzM, int(i0.niter), int(i0.inner_iters), n_z,
+        int(i0.n_refinements), int(i0.n_spmv_h))
+    t = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    avg_ms = float(t.item())
+    peak, peak_src = peaks()
+    achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
+    x_all = S.gather(dx.download())
+    feas = float(np.linalg.norm(A.dot(x_all) + b) / np.linalg.norm(b))
+    if rank == 0:
+        cfg = workload_config(args)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": size,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg, "clocks": clocks,
+            "e2e": {"value": e2e_iters / t_e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": 8 * (n + m), "d2h_bytes_per_step": 8 * n + 96 * size,
+                    "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "note": "per rank: pinned host blocks of c, b uploaded, solve, block of x "
+                            "downloaded; bytes are summed over the ranks"},
+            "gpu_launches": int(launches) * size,
+            "roofline": {"bound": "hbm", "kernel": "k_projected_cg (persistent cooperative, "
+                                                    "one per rank)",
+                         "achieved": achieved, "peak": peak * size, "unit": "GB/s",
+                         "frac": achieved / (peak * size), "traffic": None,
+                         "peak_source": peak_src + " x %d GPUs" % size,
+                         "algorithmic_bytes_per_launch": bytes_launch,
+                         "avg_launch_ms": avg_ms,
+                         "inner_iters_per_launch": int(i0.inner_iters),
+                         "bytes_per_unit": parts},
+            "cpu_baseline": None,
+            "comm": {"data_path": "in-kernel NVLink peer-memory stores + flag barriers "
+                                  "(no NCCL call inside the timed region)",
+                     "ghosts_per_rank": {"n_space": [len(g) for g in S.parts["ghosts"][0]],
+                                         "m_space": [len(g) for g in S.parts["ghosts"][1]]},
+                     "global_syncs_per_inner_iteration": 2},
+            "setup_s": {"generate": t_gen, "partition_upload_connect": t_setup},
+            "result_check": {"rel_feasibility": feas},
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():

@@ -194,6 +194,39 @@ int ipb_box_sphere_intersections(ipb_ctx *ctx, int64_t n, const double *z,
                                  double trust_radius, int entire_line, double *ta,
                                  double *tb, int *intersect);
 
+/* ---- row-partitioned multi-GPU runs (one process per GPU) ---------------- */
+/* The reference is single-process (no communication
+ * backend); this is the B200-side extension north_star asks for.  Rank g owns
+ * a contiguous block of variables (n-space) and of constraints (m-space); all
+ * solver vectors of a rank live in a symmetric arena laid out
+ * [ghost_lo | own | ghost_hi], matrices are given per rank with column indices
+ * relative to the own block (negative / past the end = ghost entries).  Inside
+ * the kernels the owners push ghost entries to their peers over NVLink peer
+ * memory before each product, and reductions go through per-rank mailboxes in
+ * peer memory, summed in rank order (bit-identical on all ranks).
+ *   own / own_max / ghost_lo / ghost_hi : 2 entries each, [0] n-space, [1] m-space
+ *     (own: this rank's block length; own_max, ghost_*: maxima over the ranks,
+ *     identical on all ranks; ghost_lo even)
+ *   n_minus_m_global : n - m of the whole problem (iteration cap, qp_subproblem.py:537)
+ *   ipc_handle_out   : 64 bytes to be all-gathered and passed to ipb_comm_connect
+ * Host-vector entry points are single-GPU; partitioned runs use *_dev calls. */
+int ipb_comm_init(ipb_ctx *ctx, int rank, int size, const int64_t *own,
+                  const int64_t *own_max, const int64_t *ghost_lo, const int64_t *ghost_hi,
+                  int64_t n_minus_m_global, int64_t arena_bytes, void *ipc_handle_out);
+int ipb_comm_connect(ipb_ctx *ctx, const void *handles /* size x 64 bytes, rank order */);
+/* entries: count x {own index, peer rank, index on the peer (own-relative), 0} (int32) */
+int ipb_comm_set_send_list(ipb_ctx *ctx, int space, int64_t count, const int32_t *entries);
+/* vector space of a matrix's columns (0: n-space, 1: m-space) -- selects the halo list */
+int ipb_csr_set_space(ipb_ctx *ctx, ipb_csr *m, int space);
+/* projector from this rank's parts (created with with_transpose = 0): rows of A
+ * (raw and row-normalised values), rows of A' for the own variables (raw and
+ * normalised), optionally the own rows of M = A~ A~'; dscale = 1/||a_i|| of
+ * the own rows, fro = ||A||_F of the whole matrix. */
+int ipb_proj_create_parts(ipb_ctx *ctx, ipb_csr *A_raw, ipb_csr *A_norm, ipb_csr *At_raw,
+                          ipb_csr *At_norm, ipb_csr *M, const double *dscale, double fro,
+                          double orth_tol, int max_refin, double inner_rtol, int inner_maxit,
+                          ipb_proj **out);
+
 /* ---- device vectors ------------------------------------------------------ */
 int ipb_vec_create(ipb_ctx *ctx, int64_t len, ipb_vec **out);
 int ipb_vec_destroy(ipb_ctx *ctx, ipb_vec *v);
@@ -215,7 +248,8 @@ int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x,
 
 /* Repeats ONE phase of the inner iteration ``reps`` times inside one launch,
  * a grid barrier after each (0: fused vector update, 1: A' r, 2: A t, 3: M r,
- * 4: barrier only, 5: the bulk-copy pipeline of M r without the arithmetic);
+ * 4: barrier only, 5: the bulk-copy pipeline of M r without the arithmetic,
+ * 6: barrier + cross-GPU all-reduce, 7: barrier + ghost push of an m-vector);
  * returns device milliseconds.  Results are discarded and
  * the projector's work vectors are overwritten. */
 int ipb_bench_phase(ipb_ctx *ctx, ipb_proj *p, int phase, int reps, double *ms);

@@ -23,6 +23,7 @@ struct ipb_vec {
 };
 
 struct ipb_csr {
+    int space = 0;                  // vector space of the columns (0: n, 1: m)
     int rows = 0, cols = 0;
     int64_t nnz = 0;
     int *rowptr = nullptr, *col = nullptr;
@@ -45,6 +46,12 @@ struct ipb_hess {
 
 struct ipb_proj {
     ipb_csr *A = nullptr;
+    int64_t m = 0, n = 0;                          // own rows of A / own columns
+    // "parts" mode (row-partitioned multi-GPU): the five local matrices are
+    // given explicitly, already in local column numbering
+    bool parts = false;
+    ipb_csr *pA_raw = nullptr, *pA_norm = nullptr, *pAt_raw = nullptr, *pAt_norm = nullptr,
+            *pM = nullptr;
     double *nval = nullptr, *nt_val = nullptr;     // row-normalised A and A'
     double *dscale = nullptr, *dnorm2 = nullptr;
     double fro = 0.0;
@@ -81,7 +88,21 @@ struct ipb_ctx {
     size_t cub_tmp_bytes = 0;
     int64_t launches = 0;
     std::string err;
+    // ---- multi-GPU (ipb_comm_*): symmetric arena + peer mappings
+    int rank = 0, size = 1;
+    char *arena = nullptr;             // [mailbox | flags | seq | vectors]
+    size_t arena_bytes = 0, arena_used = 0, arena_vec0 = 0;
+    char *peer_base[MAX_RANKS] = {nullptr};
+    int64_t own[2] = {0, 0}, own_max[2] = {0, 0}, glo[2] = {0, 0}, ghi[2] = {0, 0};
+    int4 *send_ent[2] = {nullptr, nullptr};
+    int send_cnt[2] = {0, 0};
+    int64_t nm_global = -1;
+    double *dws_n[7] = {nullptr}, *dws_m = nullptr;          // workspace vectors (dist)
+    double *dst_n[4] = {nullptr}, *dst_m = nullptr;          // host-staging vectors (dist)
 };
+
+static const size_t MBOX_BYTES = 4 * MAX_RANKS * NSLOT * 2 * sizeof(unsigned long long);
+static const size_t FLAG_OFF = MBOX_BYTES, SEQ_OFF = FLAG_OFF + 256, VEC_OFF = SEQ_OFF + 256;
 
 #define IPB_FAIL(ctx, code, ...)                                              \
     do {                                                                      \
@@ -123,15 +144,51 @@ static int dalloc(ipb_ctx *ctx, T **p, size_t count) {
 
 static SyncView sync_view(const ipb_ctx *ctx) {
     SyncView s;
+    memset(&s, 0, sizeof s);
     s.barrier = ctx->barrier;
     s.partials = ctx->partials;
     s.abort_flag = ctx->abort_flag;
+    s.C.rank = ctx->rank; s.C.size = ctx->size;
+    if (ctx->size > 1) {
+        s.C.arena = (double *)ctx->arena;
+        s.C.mbox = (double *)ctx->arena;
+        s.C.flag = (unsigned *)(ctx->arena + FLAG_OFF);
+        s.C.seq = (unsigned *)(ctx->arena + SEQ_OFF);
+        for (int q = 0; q < ctx->size; ++q) {
+            s.C.peer_arena[q] = (double *)ctx->peer_base[q];
+            s.C.peer_mbox[q] = (double *)ctx->peer_base[q];
+            s.C.peer_flag[q] = (unsigned *)(ctx->peer_base[q] + FLAG_OFF);
+        }
+        for (int k = 0; k < 2; ++k) { s.C.send[k].ent = ctx->send_ent[k]; s.C.send[k].count = ctx->send_cnt[k]; }
+    }
     return s;
+}
+
+// A solver vector of ``len`` own entries.  Single GPU: its own allocation.
+// Multi-GPU: carved from the symmetric arena as [ghost_lo | own | ghost_hi]
+// (class = n- or m-space by its length); the returned pointer is the own part.
+static int valloc(ipb_ctx *ctx, double **p, int64_t len) {
+    if (ctx->size == 1) return dalloc(ctx, p, (size_t)len + PAD);
+    int k = (len == ctx->own[0]) ? 0 : (len == ctx->own[1] ? 1 : -1);
+    if (k < 0)
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "distributed vectors must have the rank's own n (%lld) or m (%lld) "
+                 "length, got %lld", (long long)ctx->own[0], (long long)ctx->own[1], (long long)len);
+    size_t stride = (((size_t)(ctx->glo[k] + ctx->own_max[k] + ctx->ghi[k]) + PAD + 31) & ~(size_t)31) * 8;
+    if (ctx->arena_used + stride > ctx->arena_bytes)
+        IPB_FAIL(ctx, IPB_ERR_NOMEM, "symmetric arena exhausted (%zu of %zu bytes)", ctx->arena_used,
+                 ctx->arena_bytes);
+    *p = (double *)(ctx->arena + ctx->arena_used) + ctx->glo[k];
+    ctx->arena_used += stride;
+    return IPB_OK;
+}
+static void vfree(ipb_ctx *ctx, double *p) {
+    if (ctx && ctx->size > 1) return;          // arena memory is released with the context
+    cudaFree(p);
 }
 
 static CsrView csr_view(const ipb_csr *m, const double *val_override = nullptr) {
     CsrView v;
-    v.rows = m->rows; v.cols = m->cols; v.nblk = m->nblk; v.desc = m->desc;
+    v.rows = m->rows; v.cols = m->cols; v.nblk = m->nblk; v.desc = m->desc; v.space = m->space;
     v.rowptr = m->rowptr; v.col = m->col;
     v.val = val_override ? val_override : m->val;
     return v;
@@ -139,7 +196,7 @@ static CsrView csr_view(const ipb_csr *m, const double *val_override = nullptr) 
 
 static CsrView csr_view_t(const ipb_csr *m, const double *val_override = nullptr) {
     CsrView v;
-    v.rows = m->cols; v.cols = m->rows; v.nblk = m->t_nblk; v.desc = m->t_desc;
+    v.rows = m->cols; v.cols = m->rows; v.nblk = m->t_nblk; v.desc = m->t_desc; v.space = 1 - m->space;
     v.rowptr = m->t_rowptr; v.col = m->t_col;
     v.val = val_override ? val_override : m->t_val;
     return v;
@@ -288,6 +345,9 @@ extern "C" int ipb_ctx_destroy(ipb_ctx *ctx) {
     cudaFree(ctx->barrier); cudaFree(ctx->partials); cudaFree(ctx->abort_flag);
     cudaFree(ctx->d_result); cudaFreeHost(ctx->h_result);
     cudaFree(ctx->ws); cudaFree(ctx->stage); cudaFree(ctx->cub_tmp);
+    for (int q = 0; q < ctx->size; ++q)
+        if (q != ctx->rank && ctx->peer_base[q]) cudaIpcCloseMemHandle(ctx->peer_base[q]);
+    cudaFree(ctx->arena); cudaFree(ctx->send_ent[0]); cudaFree(ctx->send_ent[1]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -338,14 +398,13 @@ extern "C" int ipb_vec_create(ipb_ctx *ctx, int64_t len, ipb_vec **out) {
     if (!ctx || !out || len < 0) return IPB_ERR_INVALID;
     ipb_vec *v = new ipb_vec();
     v->len = len;
-    int s = dalloc(ctx, &v->d, (size_t)len + PAD);      // slack: bulk copies round sizes up
+    int s = valloc(ctx, &v->d, len);           // slack behind it: bulk copies round sizes up
     if (s != IPB_OK) { delete v; return s; }
     *out = v;
     return IPB_OK;
 }
 extern "C" int ipb_vec_destroy(ipb_ctx *ctx, ipb_vec *v) {
-    (void)ctx;
-    if (v) { cudaFree(v->d); delete v; }
+    if (v) { vfree(ctx, v->d); delete v; }
     return IPB_OK;
 }
 extern "C" int ipb_vec_upload(ipb_ctx *ctx, ipb_vec *v, const double *host) {
@@ -484,8 +543,16 @@ static int run_matvec(ipb_ctx *ctx, const CsrView &M, const double *dx, double *
     return launch_coop(ctx, k_matvec, a, grid, nullptr);
 }
 
+#define SINGLE_GPU_ONLY(ctx)                                                         \
+    do {                                                                             \
+        if ((ctx)->size > 1)                                                         \
+            IPB_FAIL(ctx, IPB_ERR_INVALID, "%s takes host vectors and is single-GPU; " \
+                     "row-partitioned runs use the *_dev entry points", __func__);   \
+    } while (0)
+
 static int host_in_out(ipb_ctx *ctx, int64_t nin, int64_t nout, const double *hin,
                        double **din, double **dout) {
+    SINGLE_GPU_ONLY(ctx);
     CHECK(ensure_stage(ctx, vstride(nin) + vstride(nout)));
     *din = ctx->stage; *dout = ctx->stage + vstride(nin);
     if (nin) CU(ctx, cudaMemcpyAsync(*din, hin, (size_t)nin * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -564,7 +631,7 @@ extern "C" int ipb_hess_create(ipb_ctx *ctx, int64_t n, int64_t n_x, ipb_hess **
 }
 extern "C" int ipb_hess_set_csr(ipb_ctx *ctx, ipb_hess *h, ipb_csr *s) {
     if (!ctx || !h) return IPB_ERR_INVALID;
-    if (s && (s->rows != h->nx || s->cols != h->nx))
+    if (s && (s->rows != h->nx || (ctx->size == 1 && s->cols != h->nx)))
         IPB_FAIL(ctx, IPB_ERR_INVALID, "Hessian CSR term must be n_x by n_x");
     h->S = s;
     return IPB_OK;
@@ -709,6 +776,7 @@ static int build_aat_pattern(ipb_ctx *ctx, ipb_proj *p) {
 
 extern "C" int ipb_proj_refresh(ipb_ctx *ctx, ipb_proj *p) {
     if (!ctx || !p) return IPB_ERR_INVALID;
+    if (p->parts) return IPB_OK;       // the host supplies refreshed parts
     ipb_csr *A = p->A;
     double s = 0.0;
     if (A->rows > 0) {
@@ -733,12 +801,23 @@ extern "C" int ipb_proj_refresh(ipb_ctx *ctx, ipb_proj *p) {
     return IPB_OK;
 }
 
+static int proj_vectors(ipb_ctx *ctx, ipb_proj *p) {
+    CHECK(valloc(ctx, &p->v, p->m)); CHECK(valloc(ctx, &p->r, p->m));
+    CHECK(valloc(ctx, &p->w, p->m)); CHECK(valloc(ctx, &p->p, p->m));
+    CHECK(valloc(ctx, &p->s, p->m)); CHECK(valloc(ctx, &p->rhs, p->m));
+    CHECK(valloc(ctx, &p->t, p->n));
+    return IPB_OK;
+}
+
 extern "C" int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int max_refin,
                                double inner_rtol, int inner_maxit, ipb_proj **out) {
     if (!ctx || !A || !out) return IPB_ERR_INVALID;
     if (!A->has_t) IPB_FAIL(ctx, IPB_ERR_INVALID, "projector needs A created with_transpose");
     ipb_proj *p = new ipb_proj();
     p->A = A;
+    p->m = A->rows; p->n = A->cols;
+    if (ctx->size > 1)
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "row-partitioned runs create the projector with ipb_proj_create_parts");
     p->orth_tol = orth_tol; p->max_refin = max_refin;
     p->rtol = inner_rtol > 0 ? inner_rtol : 1e-13;
     p->maxit = inner_maxit > 0 ? inner_maxit : 1000;
@@ -747,10 +826,7 @@ extern "C" int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int ma
     CHECK(dalloc(ctx, &p->nt_val, nnz + PAD));
     CHECK(dalloc(ctx, &p->dscale, m));
     CHECK(dalloc(ctx, &p->dnorm2, m));
-    CHECK(dalloc(ctx, &p->v, m + PAD)); CHECK(dalloc(ctx, &p->r, m + PAD));
-    CHECK(dalloc(ctx, &p->w, m + PAD)); CHECK(dalloc(ctx, &p->p, m + PAD));
-    CHECK(dalloc(ctx, &p->s, m + PAD)); CHECK(dalloc(ctx, &p->rhs, m + PAD));
-    CHECK(dalloc(ctx, &p->t, n + PAD));
+    CHECK(proj_vectors(ctx, p));
     const char *env = getenv("IPB_EXPLICIT_AAT");      // 0 auto, 1 never, 2 always
     if (env) p->aat_mode = atoi(env);
     CHECK(build_aat_pattern(ctx, p));
@@ -761,21 +837,22 @@ extern "C" int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int ma
 
 extern "C" int ipb_proj_set_aat_mode(ipb_ctx *ctx, ipb_proj *p, int mode) {
     if (!ctx || !p || mode < 0 || mode > 2) return IPB_ERR_INVALID;
+    if (p->parts) IPB_FAIL(ctx, IPB_ERR_INVALID, "a projector built from parts holds M iff it was given");
     p->aat_mode = mode;
     CHECK(build_aat_pattern(ctx, p));
     return ipb_proj_refresh(ctx, p);
 }
 
 extern "C" int64_t ipb_proj_aat_nnz(const ipb_proj *p) {
+    if (p && p->parts) return p->pM ? p->pM->nnz : -1;
     return (p && p->has_M) ? p->m_nnz : -1;
 }
 
 extern "C" int ipb_proj_destroy(ipb_ctx *ctx, ipb_proj *p) {
-    (void)ctx;
     if (!p) return IPB_OK;
     cudaFree(p->nval); cudaFree(p->nt_val); cudaFree(p->dscale); cudaFree(p->dnorm2);
-    cudaFree(p->v); cudaFree(p->r); cudaFree(p->w); cudaFree(p->p); cudaFree(p->s);
-    cudaFree(p->rhs); cudaFree(p->t);
+    vfree(ctx, p->v); vfree(ctx, p->r); vfree(ctx, p->w); vfree(ctx, p->p); vfree(ctx, p->s);
+    vfree(ctx, p->rhs); vfree(ctx, p->t);
     free_aat(p);
     delete p;
     return IPB_OK;
@@ -784,11 +861,24 @@ extern "C" int ipb_proj_destroy(ipb_ctx *ctx, ipb_proj *p) {
 static ProjView proj_view(const ipb_proj *p) {
     ProjView v;
     memset(&v, 0, sizeof v);
-    v.m = p->A->rows; v.n = p->A->cols;
+    v.m = (int)p->m; v.n = (int)p->n;
+    v.dscale = p->dscale; v.dnorm2 = p->dnorm2;
+    v.fro = p->fro; v.orth_tol = p->orth_tol; v.max_refin = p->max_refin;
+    v.rtol = p->rtol; v.maxit = p->maxit;
+    v.v = p->v; v.r = p->r; v.w = p->w; v.p = p->p; v.s = p->s; v.rhs = p->rhs; v.t = p->t;
+    if (p->parts) {
+        v.A = csr_view(p->pA_norm);
+        v.At = csr_view(p->pAt_norm);
+        v.has_M = p->pM ? 1 : 0;
+        if (p->pM) v.M = csr_view(p->pM);
+        v.Araw = p->pA_raw->val;
+        return v;
+    }
     v.A = csr_view(p->A, p->nval);
     v.At = csr_view_t(p->A, p->nt_val);
     v.has_M = p->has_M ? 1 : 0;
     if (p->has_M) {
+        v.M.space = 1;
         v.M.rows = v.m; v.M.cols = v.m; v.M.nblk = p->m_nblk; v.M.desc = p->m_desc;
         v.M.rowptr = p->m_rowptr; v.M.col = p->m_col; v.M.val = p->m_val;
     }
@@ -801,7 +891,7 @@ static ProjView proj_view(const ipb_proj *p) {
 }
 
 static int proj_grid(const ipb_ctx *ctx, const ipb_proj *p) {
-    return grid_for(ctx, std::max<int64_t>(p->A->cols, 1) * 4);
+    return grid_for(ctx, std::max<int64_t>(p->n, 1) * 4);
 }
 
 static int run_proj(ipb_ctx *ctx, ipb_proj *p, int op, const double *din, double *dout,
@@ -828,24 +918,24 @@ static int run_proj(ipb_ctx *ctx, ipb_proj *p, int op, const double *din, double
 
 extern "C" int ipb_proj_null_space_dev(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x, ipb_vec *z,
                                        ipb_proj_info *info) {
-    if (!ctx || !p || !x || !z || x->len != p->A->cols || z->len != p->A->cols) return IPB_ERR_INVALID;
+    if (!ctx || !p || !x || !z || x->len != p->n || z->len != p->n) return IPB_ERR_INVALID;
     return run_proj(ctx, p, 0, x->d, z->d, 0, info);
 }
 extern "C" int ipb_proj_least_squares_dev(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x, ipb_vec *v,
                                           ipb_proj_info *info) {
-    if (!ctx || !p || !x || !v || x->len != p->A->cols || v->len != p->A->rows) return IPB_ERR_INVALID;
+    if (!ctx || !p || !x || !v || x->len != p->n || v->len != p->m) return IPB_ERR_INVALID;
     return run_proj(ctx, p, 1, x->d, v->d, 0, info);
 }
 extern "C" int ipb_proj_row_space_dev(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *b, ipb_vec *y,
                                       ipb_proj_info *info) {
-    if (!ctx || !p || !b || !y || b->len != p->A->rows || y->len != p->A->cols) return IPB_ERR_INVALID;
+    if (!ctx || !p || !b || !y || b->len != p->m || y->len != p->n) return IPB_ERR_INVALID;
     return run_proj(ctx, p, 2, b->d, y->d, 0, info);
 }
 
 extern "C" int ipb_proj_null_space(ipb_ctx *ctx, ipb_proj *p, const double *x, double *z,
                                    ipb_proj_info *info) {
     if (!ctx || !p) return IPB_ERR_INVALID;
-    int64_t n = p->A->cols;
+    int64_t n = p->n;
     double *din, *dout;
     CHECK(host_in_out(ctx, n, n, x, &din, &dout));
     CHECK(run_proj(ctx, p, 0, din, dout, 0, info));
@@ -854,7 +944,7 @@ extern "C" int ipb_proj_null_space(ipb_ctx *ctx, ipb_proj *p, const double *x, d
 extern "C" int ipb_proj_least_squares(ipb_ctx *ctx, ipb_proj *p, const double *x, double *v,
                                       ipb_proj_info *info) {
     if (!ctx || !p) return IPB_ERR_INVALID;
-    int64_t n = p->A->cols, m = p->A->rows;
+    int64_t n = p->n, m = p->m;
     double *din, *dout;
     CHECK(host_in_out(ctx, n, m, x, &din, &dout));
     CHECK(run_proj(ctx, p, 1, din, dout, 0, info));
@@ -863,7 +953,7 @@ extern "C" int ipb_proj_least_squares(ipb_ctx *ctx, ipb_proj *p, const double *x
 extern "C" int ipb_proj_row_space(ipb_ctx *ctx, ipb_proj *p, const double *b, double *y,
                                   ipb_proj_info *info) {
     if (!ctx || !p) return IPB_ERR_INVALID;
-    int64_t n = p->A->cols, m = p->A->rows;
+    int64_t n = p->n, m = p->m;
     double *din, *dout;
     CHECK(host_in_out(ctx, m, n, b, &din, &dout));
     CHECK(run_proj(ctx, p, 2, din, dout, 0, info));
@@ -871,7 +961,7 @@ extern "C" int ipb_proj_row_space(ipb_ctx *ctx, ipb_proj *p, const double *b, do
 }
 extern "C" int ipb_orthogonality(ipb_ctx *ctx, ipb_proj *p, const double *g, double *out) {
     if (!ctx || !p || !out) return IPB_ERR_INVALID;
-    int64_t n = p->A->cols;
+    int64_t n = p->n;
     double *din, *dout;
     CHECK(host_in_out(ctx, n, 0, g, &din, &dout));
     ipb_proj_info info;
@@ -882,7 +972,7 @@ extern "C" int ipb_orthogonality(ipb_ctx *ctx, ipb_proj *p, const double *g, dou
 
 extern "C" int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x, int iters,
                                           double *ms) {
-    if (!ctx || !p || !x || iters <= 0 || x->len != p->A->cols) return IPB_ERR_INVALID;
+    if (!ctx || !p || !x || iters <= 0 || x->len != p->n) return IPB_ERR_INVALID;
     ipb_proj_info info;
     CHECK(run_proj(ctx, p, 4, x->d, nullptr, iters, &info));
     if (ms) *ms = info.kernel_ms;
@@ -890,10 +980,20 @@ extern "C" int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_v
 }
 
 extern "C" int ipb_bench_phase(ipb_ctx *ctx, ipb_proj *p, int phase, int reps, double *ms) {
-    if (!ctx || !p || reps <= 0 || phase < 0 || phase > 5) return IPB_ERR_INVALID;
+    if (!ctx || !p || reps <= 0 || phase < 0 || phase > 7) return IPB_ERR_INVALID;
     ipb_proj_info info;
     CHECK(run_proj(ctx, p, 10 + phase, p->rhs, nullptr, reps, &info));
     if (ms) *ms = info.kernel_ms;
+    return IPB_OK;
+}
+
+// workspace vectors of a row-partitioned context (allocated once, same order on every rank)
+static int dist_workspace(ipb_ctx *ctx) {
+    if (ctx->dws_m) return IPB_OK;
+    if (ctx->nm_global < 0)
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "call ipb_comm_init before solving on a row-partitioned context");
+    for (int k = 0; k < 7; ++k) CHECK(valloc(ctx, &ctx->dws_n[k], ctx->own[0]));
+    CHECK(valloc(ctx, &ctx->dws_m, ctx->own[1]));
     return IPB_OK;
 }
 
@@ -902,11 +1002,12 @@ static int run_pcg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, const double *d
                    const double *db, double radius, const double *dlb, const double *dub,
                    double tol, int64_t max_iter, int64_t max_inf, double *dx_out,
                    double *d_allvecs, int64_t allvecs_cap, ipb_pcg_info *info) {
-    const int64_t n = P->A->cols, m = P->A->rows;
+    const int64_t n = P->n, m = P->m;
     if (H->n != n) IPB_FAIL(ctx, IPB_ERR_INVALID, "H is %lld x %lld but A has %lld columns",
                             (long long)H->n, (long long)H->n, (long long)n);
     const size_t ns = vstride(n);
-    CHECK(ensure_ws(ctx, 7 * ns));
+    if (ctx->size == 1) CHECK(ensure_ws(ctx, 7 * ns));
+    else CHECK(dist_workspace(ctx));
     PcgArgs a;
     memset(&a, 0, sizeof a);
     a.H = hess_view(H); a.P = proj_view(P); a.S = sync_view(ctx);
@@ -916,8 +1017,14 @@ static int run_pcg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, const double *d
     a.radius = radius; a.tol = tol;
     a.max_iter = max_iter; a.max_infeasible = max_inf;
     double *w = ctx->ws;
-    a.x = w; a.xn = w + ns; a.r = w + 2 * ns; a.p = w + 3 * ns; a.Hp = w + 4 * ns;
-    a.xfeas = w + 5 * ns; a.tmp = w + 6 * ns;
+    if (ctx->size == 1) {
+        a.x = w; a.xn = w + ns; a.r = w + 2 * ns; a.p = w + 3 * ns; a.Hp = w + 4 * ns;
+        a.xfeas = w + 5 * ns; a.tmp = w + 6 * ns;
+    } else {
+        double **d = ctx->dws_n;
+        a.x = d[0]; a.xn = d[1]; a.r = d[2]; a.p = d[3]; a.Hp = d[4]; a.xfeas = d[5]; a.tmp = d[6];
+    }
+    a.nm_global = ctx->size > 1 ? ctx->nm_global : (long long)n - m;
     a.allvecs = d_allvecs; a.allvecs_cap = allvecs_cap;
     a.result = (PcgArgs::Result *)ctx->d_result;
     float ms = 0.f;
@@ -951,7 +1058,7 @@ extern "C" int ipb_projected_cg_dev(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P
                                     int64_t max_iter, int64_t max_infeasible_iter,
                                     ipb_vec *x, ipb_pcg_info *info) {
     if (!ctx || !H || !P || !c || !b || !x) return IPB_ERR_INVALID;
-    const int64_t n = P->A->cols, m = P->A->rows;
+    const int64_t n = P->n, m = P->m;
     if (c->len != n || b->len != m || x->len != n || (lb && lb->len != n) || (ub && ub->len != n))
         IPB_FAIL(ctx, IPB_ERR_INVALID, "projected_cg: vector lengths do not match A");
     int s = run_pcg(ctx, H, P, c->d, b->d, trust_radius, lb ? lb->d : nullptr,
@@ -966,7 +1073,8 @@ extern "C" int ipb_projected_cg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, co
                                 int64_t max_infeasible_iter, double *x, double *allvecs,
                                 int64_t allvecs_cap, ipb_pcg_info *info) {
     if (!ctx || !H || !P || !c || !b || !x) return IPB_ERR_INVALID;
-    const int64_t n = P->A->cols, m = P->A->rows;
+    SINGLE_GPU_ONLY(ctx);
+    const int64_t n = P->n, m = P->m;
     const bool box = lb && ub;
     if (!allvecs) allvecs_cap = 0;
     const size_t ns = vstride(n), ms = vstride(m);
@@ -998,7 +1106,8 @@ extern "C" int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b, d
                                    const double *lb, const double *ub, double *x,
                                    ipb_proj_info *info) {
     if (!ctx || !P || !b || !x) return IPB_ERR_INVALID;
-    const int64_t n = P->A->cols, m = P->A->rows;
+    SINGLE_GPU_ONLY(ctx);
+    const int64_t n = P->n, m = P->m;
     const bool box = lb && ub;
     const size_t ns = vstride(n), mstr = vstride(m);
     CHECK(ensure_stage(ctx, mstr + (box ? 2 * ns : 0)));
@@ -1012,7 +1121,8 @@ extern "C" int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b, d
     DoglegArgs a;
     memset(&a, 0, sizeof a);
     a.P = proj_view(P); a.S = sync_view(ctx);
-    a.Araw = csr_view(P->A); a.Atraw = csr_view_t(P->A);
+    if (P->parts) { a.Araw = csr_view(P->pA_raw); a.Atraw = csr_view(P->pAt_raw); }
+    else { a.Araw = csr_view(P->A); a.Atraw = csr_view_t(P->A); }
     a.n = (int)n; a.m = (int)m; a.b = db; a.lb = box ? dlb : nullptr; a.ub = box ? dub : nullptr;
     a.has_box = box; a.radius = trust_radius;
     double *w = ctx->ws;
@@ -1041,6 +1151,7 @@ extern "C" int ipb_box_sphere_intersections(ipb_ctx *ctx, int64_t n, const doubl
                                             double trust_radius, int entire_line, double *ta,
                                             double *tb, int *intersect) {
     if (!ctx || !z || !d || !ta || !tb || !intersect || n < 0) return IPB_ERR_INVALID;
+    SINGLE_GPU_ONLY(ctx);
     const bool box = lb && ub;
     CHECK(ensure_stage(ctx, (size_t)n * (box ? 4 : 2)));
     double *dz = ctx->stage, *dd = dz + n, *dlb = dd + n, *dub = dlb + (box ? n : 0);
@@ -1063,5 +1174,91 @@ extern "C" int ipb_box_sphere_intersections(ipb_ctx *ctx, int64_t n, const doubl
     CU(ctx, cudaMemcpyAsync(h, ctx->d_result, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     *ta = h->ta; *tb = h->tb; *intersect = h->hit;
+    return IPB_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU
+extern "C" int ipb_csr_set_space(ipb_ctx *ctx, ipb_csr *m, int space) {
+    if (!ctx || !m || space < 0 || space > 1) return IPB_ERR_INVALID;
+    m->space = space;
+    return IPB_OK;
+}
+
+extern "C" int ipb_comm_init(ipb_ctx *ctx, int rank, int size, const int64_t *own,
+                             const int64_t *own_max, const int64_t *ghost_lo,
+                             const int64_t *ghost_hi, int64_t n_minus_m_global,
+                             int64_t arena_bytes, void *ipc_handle_out) {
+    if (!ctx || size < 1 || size > MAX_RANKS || rank < 0 || rank >= size || !own || !own_max ||
+        !ghost_lo || !ghost_hi || !ipc_handle_out)
+        return IPB_ERR_INVALID;
+    if (ctx->arena) IPB_FAIL(ctx, IPB_ERR_INVALID, "ipb_comm_init called twice");
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (int k = 0; k < 2; ++k) {
+        if (ghost_lo[k] & 1) IPB_FAIL(ctx, IPB_ERR_INVALID, "ghost_lo must be even (16-byte alignment)");
+        ctx->own[k] = own[k]; ctx->own_max[k] = own_max[k];
+        ctx->glo[k] = ghost_lo[k]; ctx->ghi[k] = ghost_hi[k];
+    }
+    ctx->rank = rank; ctx->size = size; ctx->nm_global = n_minus_m_global;
+    ctx->arena_bytes = ((size_t)arena_bytes + VEC_OFF + 4095) & ~(size_t)4095;
+    CU(ctx, cudaMalloc((void **)&ctx->arena, ctx->arena_bytes));
+    CU(ctx, cudaMemset(ctx->arena, 0, ctx->arena_bytes));
+    ctx->arena_used = VEC_OFF;
+    cudaIpcMemHandle_t h;
+    CU(ctx, cudaIpcGetMemHandle(&h, ctx->arena));
+    memcpy(ipc_handle_out, &h, sizeof h);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (size == 1) ctx->peer_base[0] = ctx->arena;
+    return IPB_OK;
+}
+
+extern "C" int ipb_comm_connect(ipb_ctx *ctx, const void *handles) {
+    if (!ctx || !handles || !ctx->arena) return IPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (int q = 0; q < ctx->size; ++q) {
+        if (q == ctx->rank) { ctx->peer_base[q] = ctx->arena; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)q, sizeof h);
+        void *p = nullptr;
+        CU(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_base[q] = (char *)p;
+    }
+    return IPB_OK;
+}
+
+extern "C" int ipb_comm_set_send_list(ipb_ctx *ctx, int space, int64_t count, const int32_t *entries) {
+    if (!ctx || space < 0 || space > 1 || count < 0 || (count && !entries)) return IPB_ERR_INVALID;
+    cudaFree(ctx->send_ent[space]);
+    ctx->send_ent[space] = nullptr; ctx->send_cnt[space] = 0;
+    if (count) {
+        CHECK(dalloc(ctx, &ctx->send_ent[space], (size_t)count));
+        CU(ctx, cudaMemcpy(ctx->send_ent[space], entries, (size_t)count * sizeof(int4), cudaMemcpyHostToDevice));
+        ctx->send_cnt[space] = (int)count;
+    }
+    return IPB_OK;
+}
+
+extern "C" int ipb_proj_create_parts(ipb_ctx *ctx, ipb_csr *A_raw, ipb_csr *A_norm, ipb_csr *At_raw,
+                                     ipb_csr *At_norm, ipb_csr *M, const double *dscale,
+                                     double fro, double orth_tol, int max_refin,
+                                     double inner_rtol, int inner_maxit, ipb_proj **out) {
+    if (!ctx || !A_raw || !A_norm || !At_raw || !At_norm || !out || (A_raw->rows && !dscale))
+        return IPB_ERR_INVALID;
+    if (A_norm->rows != A_raw->rows || A_norm->nnz != A_raw->nnz || At_norm->rows != At_raw->rows ||
+        (M && M->rows != A_raw->rows))
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "ipb_proj_create_parts: inconsistent parts");
+    ipb_proj *p = new ipb_proj();
+    p->parts = true;
+    p->pA_raw = A_raw; p->pA_norm = A_norm; p->pAt_raw = At_raw; p->pAt_norm = At_norm; p->pM = M;
+    A_raw->space = 0; A_norm->space = 0; At_raw->space = 1; At_norm->space = 1;
+    if (M) M->space = 1;
+    p->m = A_raw->rows; p->n = At_raw->rows;
+    p->fro = fro; p->orth_tol = orth_tol; p->max_refin = max_refin;
+    p->rtol = inner_rtol > 0 ? inner_rtol : 1e-13;
+    p->maxit = inner_maxit > 0 ? inner_maxit : 1000;
+    CHECK(dalloc(ctx, &p->dscale, (size_t)p->m));
+    CHECK(dalloc(ctx, &p->dnorm2, (size_t)p->m));
+    if (p->m) CU(ctx, cudaMemcpy(p->dscale, dscale, (size_t)p->m * 8, cudaMemcpyHostToDevice));
+    CHECK(proj_vectors(ctx, p));
+    *out = p;
     return IPB_OK;
 }

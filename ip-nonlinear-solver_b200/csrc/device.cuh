@@ -59,6 +59,7 @@ enum { OP_SUM = 0, OP_MIN = 1, OP_MAX = 2 };
 // ---------------------------------------------------------------- structs
 struct CsrView {
     int rows, cols;
+    int space;                // vector space of the columns (0: n, 1: m) -- selects the halo list
     int nblk;                 // row blocks (built at upload, <= CHUNK nnz each)
     const int4 *desc;         // per block {r0, r1, p0, len}, {c0, xcnt, -, -}
     const int *rowptr;
@@ -74,10 +75,39 @@ struct HessView {
     const double *tail;       // n - nx
 };
 
+constexpr int MAX_RANKS = 8;
+
+// Multi-GPU state of a row-partitioned solve (one process per GPU; every
+// pointer below that belongs to a peer is a CUDA-IPC mapping of the peer's
+// allocation, reached over NVLink).  size == 1: single GPU, nothing is used.
+//   * all solver vectors of a rank live in one symmetric arena (same offsets
+//     on every rank), laid out [ghost_lo | own | ghost_hi]; a matrix's column
+//     indices are relative to the own part (negative / beyond the end = ghost);
+//   * before an SpMV the owners PUSH the entries their peers hold as ghosts
+//     (remote stores), then all ranks meet at a flag barrier;
+//   * reductions: every rank posts its partial sums into every peer's mailbox
+//     and adds the mailbox up in rank order -- bit-identical on all ranks.
+struct SendList {
+    const int4 *ent;          // {src index (own), peer, dst index on the peer (own-relative), 0}
+    int count;
+};
+struct CommView {
+    int rank, size;
+    double *arena;            // this rank's arena
+    double *peer_arena[MAX_RANKS];
+    double *mbox;             // [4][MAX_RANKS][NSLOT] in this rank's memory
+    unsigned *flag;           // [size] last sequence number posted by each rank
+    double *peer_mbox[MAX_RANKS];
+    unsigned *peer_flag[MAX_RANKS];
+    unsigned *seq;            // sequence counter of this rank (persists across launches)
+    SendList send[2];         // 0: n-space vectors, 1: m-space vectors
+};
+
 struct SyncView {
     unsigned *barrier;        // sense-reversing arrival counter
     double *partials;         // [NSLOT][MAX_GRID]
     int *abort_flag;          // set when a spin times out
+    CommView C;
 };
 
 struct ProjView {
@@ -190,8 +220,8 @@ __device__ __forceinline__ void publish(const SyncView &S, int slot, double v,
 // After a grid_sync: every CTA combines all CTAs' partials of slots
 // [0, nslots) in the same fixed order, so every thread of the grid sees
 // bit-identical values.  out: shared array of NSLOT doubles.
-__device__ __forceinline__ void collect(const SyncView &S, int nslots,
-                                        const int *ops, double *out) {
+__device__ __forceinline__ void collect_local(const SyncView &S, int nslots,
+                                              const int *ops, double *out) {
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int slot = warp; slot < nslots; slot += WARPS) {
         int op = ops[slot];
@@ -223,6 +253,7 @@ struct __align__(128) Smem {
     unsigned long long full[NSTAGE];
     unsigned done[NSTAGE];        // warps that have finished with the stage's block
     unsigned seq;                 // stage uses of this CTA so far (slot = seq % NSTAGE)
+    unsigned gseq;                // cross-GPU sequence number (multi-GPU only)
     double red[WARPS];
     double out[NSLOT];
     int ops[NSLOT];
@@ -232,8 +263,9 @@ __device__ __forceinline__ unsigned smem_addr(const void *p) {
     return (unsigned)__cvta_generic_to_shared(p);
 }
 
-__device__ __forceinline__ void pipeline_init(Smem &sm) {
+__device__ __forceinline__ void pipeline_init(Smem &sm, const SyncView &S) {
     if (threadIdx.x == 0) {
+        sm.gseq = S.C.size > 1 ? *reinterpret_cast<volatile unsigned *>(S.C.seq) : 0u;
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.full[s])));
@@ -271,6 +303,118 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *mbar, unsigned par
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long *mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(mbar)) : "memory");
+}
+
+// ---------------------------------------------------------------- cross-GPU
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0,[%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0],%1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Cross-GPU all-reduce of sm.out[0..nslots) in rank order, "LL" style: every
+// value travels as two 8-byte words {sequence number, 32 bits of the double},
+// so a word is its own arrival flag (8-byte stores are atomic over NVLink)
+// and no fence or separate flag is needed: one NVLink hop.  CTA 0 posts this
+// rank's values into every peer's mailbox; EVERY CTA polls its own rank's
+// mailbox and adds the ranks up in the same order -- bit-identical everywhere.
+// Mailbox generation = seq & 3 (a rank is never two exchanges ahead of a peer).
+__device__ __forceinline__ void rank_allreduce(const SyncView &S, Smem &sm, int nslots) {
+    const CommView &C = S.C;
+    const unsigned seq = sm.gseq + 1u;
+    const int gen = (int)(seq & 3u);
+    const int t = threadIdx.x;
+    if (blockIdx.x == 0 && t < nslots * C.size) {
+        const int slot = t % nslots, q = t / nslots;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(sm.out[slot]);
+        const unsigned long long lo = ((unsigned long long)seq << 32) | (bits & 0xffffffffull);
+        const unsigned long long hi = ((unsigned long long)seq << 32) | (bits >> 32);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(C.peer_mbox[q]) +
+                                  2 * (size_t)((gen * MAX_RANKS + C.rank) * NSLOT + slot);
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+    }
+    __syncthreads();                      // everybody has read sm.out of the local collect
+    if (t < nslots) {
+        const int op = sm.ops[t];
+        double a = 0.0;
+        for (int q = 0; q < C.size; ++q) {
+            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(C.mbox) +
+                                            2 * (size_t)((gen * MAX_RANKS + q) * NSLOT + t);
+            unsigned long long lo, hi;
+            long long spins = 0;
+            do {
+                asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+                if (++spins > (1ll << 28)) { *S.abort_flag = 3; __trap(); }
+            } while ((unsigned)(lo >> 32) != seq || (unsigned)(hi >> 32) != seq);
+            const double v = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+            a = q == 0 ? v : comb(a, v, op);
+        }
+        sm.out[t] = a;
+    }
+    if (t == 0) {
+        sm.gseq = seq;
+        if (blockIdx.x == 0) *reinterpret_cast<volatile unsigned *>(C.seq) = seq;
+    }
+    __syncthreads();
+}
+
+// Flag barrier across the ranks, with release/acquire semantics for the
+// remote stores (ghost pushes) that CTA 0 -- or, after a grid barrier, the
+// whole grid -- made before it: CTA 0 posts this sequence number into every
+// peer's flag array, every CTA waits for every rank's number.
+__device__ __forceinline__ void rank_barrier(const SyncView &S, Smem &sm) {
+    const CommView &C = S.C;
+    const unsigned seq = sm.gseq + 1u;
+    if (blockIdx.x == 0) {
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < C.size) st_release_sys(C.peer_flag[threadIdx.x] + C.rank, seq);
+        if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(C.seq) = seq;
+    }
+    if ((int)threadIdx.x < C.size) {
+        long long spins = 0;
+        while ((int)(ld_acquire_sys(C.flag + threadIdx.x) - seq) < 0)
+            if (++spins > (1ll << 28)) { *S.abort_flag = 3; __trap(); }
+    }
+    if (threadIdx.x == 0) sm.gseq = seq;
+    __syncthreads();
+}
+
+// After a grid_sync: sm.out[slot] = combination of every CTA's (and every
+// rank's) partial of slots [0, nslots), in a fixed order -- bit-identical in
+// every thread of every rank.
+__device__ __forceinline__ void collect(const SyncView &S, Smem &sm, int nslots) {
+    collect_local(S, nslots, sm.ops, sm.out);
+    if (S.C.size > 1) rank_allreduce(S, sm, nslots);
+}
+
+// Called with x final on every rank (the condition any SpMV needs anyway):
+// push the entries of x that peers hold as ghosts, then meet.  Short lists
+// are pushed by CTA 0 alone (one grid barrier less).
+__device__ __noinline__ void halo_sync(const SyncView &S, Smem &sm, const double *x, int space) {
+    const CommView &C = S.C;
+    const SendList L = C.send[space];
+    const ptrdiff_t off = x - C.arena;                 // same offset on every rank
+    const bool small = L.count <= 4 * THREADS;
+    if (small) {
+        if (blockIdx.x == 0)
+            for (int i = threadIdx.x; i < L.count; i += THREADS) {
+                const int4 e = __ldg(L.ent + i);
+                C.peer_arena[e.y][off + e.z] = x[e.x];
+            }
+    } else {
+        const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+        for (int i = gt; i < L.count; i += nt) {
+            const int4 e = __ldg(L.ent + i);
+            C.peer_arena[e.y][off + e.z] = x[e.x];
+        }
+        __threadfence_system();
+        grid_sync(S);
+    }
+    rank_barrier(S, sm);
 }
 
 // ---------------------------------------------------------------- SpMV
@@ -460,6 +604,7 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
 __device__ __forceinline__ void spmv(const CsrView M, const double *x, const Epi e,
                                      Smem &sm, const SyncView &S, double &acc0,
                                      double &acc1) {
+    if (S.C.size > 1) halo_sync(S, sm, x, M.space);
     const bool fast = !e.addv && e.sa == 1.0 && !e.accumulate && !e.want_sq &&
                       !e.post && !e.wv;
     if (fast) spmv_impl<true>(M, x, e, sm, S, acc0, acc1);
@@ -582,7 +727,7 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
     publish(S, 1, gpart, OP_SUM, sm.red);
     set_ops(sm, OP_SUM, OP_SUM);
     grid_sync(S);
-    collect(S, 2, sm.ops, sm.out);
+    collect(S, sm, 2);
     double delta = sm.out[0], gamma = sm.out[1];
     const double gamma0 = gamma;
     st.n_solves += 1;
@@ -633,7 +778,7 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
         publish(S, 0, a0, OP_SUM, sm.red);
         publish(S, 1, gpart, OP_SUM, sm.red);
         grid_sync(S);
-        collect(S, 2, sm.ops, sm.out);
+        collect(S, sm, 2);
         double delta2 = sm.out[0], gamma2 = sm.out[1];
         if (fixed_iters <= 0 && gamma2 <= target) break;
         beta = gamma2 / gamma;
@@ -666,7 +811,7 @@ __device__ __noinline__ double null_space(const ProjView &P, const SyncView &S,
         publish(S, 0, zz, OP_SUM, sm.red);
         set_ops(sm, OP_SUM);
         grid_sync(S);
-        collect(S, 1, sm.ops, sm.out);
+        collect(S, sm, 1);
         st.orth = 0.0;
         return sm.out[0];
     }
@@ -699,7 +844,7 @@ __device__ __noinline__ double null_space(const ProjView &P, const SyncView &S,
         }
         set_ops(sm, OP_SUM, OP_SUM);
         grid_sync(S);
-        collect(S, 2, sm.ops, sm.out);
+        collect(S, sm, 2);
         zz = sm.out[0];
         double az = sm.out[1];
         double orth = 0.0;
@@ -750,7 +895,7 @@ __device__ __noinline__ double row_space(const ProjView &P, const SyncView &S,
     publish(S, 0, a1, OP_SUM, sm.red);
     set_ops(sm, OP_SUM);
     grid_sync(S);
-    collect(S, 1, sm.ops, sm.out);
+    collect(S, sm, 1);
     return sm.out[0];
 }
 
@@ -825,7 +970,7 @@ __device__ __noinline__ Interval box_ball(const SyncView &S, Smem &sm, int n,
     publish(S, 5, bad, OP_MAX, sm.red);
     set_ops(sm, OP_SUM, OP_SUM, OP_SUM, OP_MAX, OP_MIN, OP_MAX);
     grid_sync(S);
-    collect(S, 6, sm.ops, sm.out);
+    collect(S, sm, 6);
     dd = sm.out[0]; zd = sm.out[1]; zz = sm.out[2];
     // norm(d) == 0 test of the reference is on sqrt(dd)
     Interval Ib;
@@ -859,6 +1004,7 @@ struct PcgArgs {
     int has_box;
     double radius, tol;                // tol < 0 or NaN: default rule
     long long max_iter, max_infeasible;
+    long long nm_global;               // n - m summed over the ranks
     // work vectors (n): x, xn, r, p, Hp, xfeas, tmp
     double *x, *xn, *r, *p, *Hp, *xfeas, *tmp;
     double *allvecs; long long allvecs_cap;
@@ -887,7 +1033,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_projected_cg(const PcgArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    pipeline_init(sm);
+    pipeline_init(sm, a.S);
     const SyncView &S = a.S;
     const int n = a.n;
     const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
@@ -907,7 +1053,7 @@ k_projected_cg(const PcgArgs a) {
     publish(S, 0, bb, OP_SUM, sm.red);
     set_ops(sm, OP_SUM);
     grid_sync(S);
-    collect(S, 1, sm.ops, sm.out);
+    collect(S, sm, 1);
     bb = sm.out[0];
     double xx = 0.0;
     if (bb > 0.0) {
@@ -940,7 +1086,7 @@ k_projected_cg(const PcgArgs a) {
     publish(S, 0, acc0, OP_SUM, sm.red);
     set_ops(sm, OP_SUM);
     grid_sync(S);
-    collect(S, 1, sm.ops, sm.out);
+    collect(S, sm, 1);
     double pHp = sm.out[0];
     double ng = sqrt(gg);
     double rt_g = ng * ng;
@@ -955,7 +1101,7 @@ k_projected_cg(const PcgArgs a) {
     }
     if (!(tol >= 0.0))                                   // default (:529-530)
         tol = fmax(fmin(0.01 * sqrt(rt_g), 0.1 * rt_g), 1e-25);
-    long long nm = (long long)n - a.m;
+    long long nm = a.nm_global;                          // n - m of the whole problem
     long long max_iter = a.max_iter < 0 ? nm : a.max_iter;
     if (max_iter > nm) max_iter = nm;
     long long max_inf = a.max_infeasible < 0 ? nm : a.max_infeasible;
@@ -997,7 +1143,7 @@ k_projected_cg(const PcgArgs a) {
             publish(S, 1, out, OP_MAX, sm.red);
             set_ops(sm, OP_SUM, OP_MAX);
             grid_sync(S);
-            collect(S, 2, sm.ops, sm.out);
+            collect(S, sm, 2);
             double nxn = sqrt(sm.out[0]);
             bool inside = !(sm.out[1] > 0.0);
             if (nxn >= a.radius) {                                   // :583-596
@@ -1041,7 +1187,7 @@ k_projected_cg(const PcgArgs a) {
             publish(S, 0, acc0, OP_SUM, sm.red);
             set_ops(sm, OP_SUM);
             grid_sync(S);
-            collect(S, 1, sm.ops, sm.out);
+            collect(S, sm, 1);
             pHp = sm.out[0];
         }
     }
@@ -1057,7 +1203,7 @@ k_projected_cg(const PcgArgs a) {
         publish(S, 0, out, OP_MAX, sm.red);
         set_ops(sm, OP_MAX);
         grid_sync(S);
-        collect(S, 1, sm.ops, sm.out);
+        collect(S, sm, 1);
         if (sm.out[0] > 0.0) { final_slot = 2; hits = 1; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1091,7 +1237,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_projector(const ProjArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    pipeline_init(sm);
+    pipeline_init(sm, a.S);
     ProjStats st = {0, 0, 0, 0, 0.0, 0.0};
     const SyncView &S = a.S;
     const ProjView &P = a.P;
@@ -1116,7 +1262,7 @@ k_projector(const ProjArgs a) {
         publish(S, 1, a1, OP_SUM, sm.red);
         set_ops(sm, OP_SUM, OP_SUM);
         grid_sync(S);
-        collect(S, 2, sm.ops, sm.out);
+        collect(S, sm, 2);
         double ng = sqrt(sm.out[0]);
         st.orth = (ng == 0.0 || P.fro == 0.0) ? 0.0 : sqrt(sm.out[1]) / (P.fro * ng);
     } else if (a.op == 4) {
@@ -1159,6 +1305,16 @@ k_projector(const ProjArgs a) {
                 spmv(P.M, P.r, e, sm, S, a0, a1);
             } else if (a.op == 15 && P.has_M) {
                 spmv(P.M, P.r, epi_plain(nullptr), sm, S, a0, a1);   // bulk copies only
+            } else if (a.op == 16) {
+                // a two-value reduction exactly as the solvers do it
+                publish(S, 0, 1.0, OP_SUM, sm.red);
+                publish(S, 1, 2.0, OP_SUM, sm.red);
+                set_ops(sm, OP_SUM, OP_SUM);
+                grid_sync(S);
+                collect(S, sm, 2);
+                a0 += sm.out[0] + sm.out[1];
+            } else if (a.op == 17) {
+                if (S.C.size > 1) halo_sync(S, sm, P.r, 1);         // + ghost push of an m-vector
             }
             grid_sync(S);
         }
@@ -1192,7 +1348,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_dogleg(const DoglegArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    pipeline_init(sm);
+    pipeline_init(sm, a.S);
     ProjStats st = {0, 0, 0, 0, 0.0, 0.0};
     const SyncView &S = a.S;
     const int n = a.n, m = a.m;
@@ -1210,7 +1366,7 @@ k_dogleg(const DoglegArgs a) {
     publish(S, 0, out, OP_MAX, sm.red);
     set_ops(sm, OP_MAX);
     grid_sync(S);
-    collect(S, 1, sm.ops, sm.out);
+    collect(S, sm, 1);
     const double *res = a.newton;
     if (!(sm.out[0] > 0.0) && sqrt(nn) <= a.radius) {
         res = a.newton;
@@ -1227,7 +1383,7 @@ k_dogleg(const DoglegArgs a) {
         publish(S, 1, a1, OP_SUM, sm.red);
         set_ops(sm, OP_SUM, OP_SUM);
         grid_sync(S);
-        collect(S, 2, sm.ops, sm.out);
+        collect(S, sm, 2);
         double coef = -sm.out[0] / sm.out[1];
         // cauchy, and step = newton - cauchy kept in x2 for now
         for (int i = gt; i < n; i += nt) {
@@ -1267,7 +1423,7 @@ k_dogleg(const DoglegArgs a) {
         publish(S, 1, a1, OP_SUM, sm.red);
         set_ops(sm, OP_SUM, OP_SUM);
         grid_sync(S);
-        collect(S, 2, sm.ops, sm.out);
+        collect(S, sm, 2);
         res = (sqrt(sm.out[0]) < sqrt(sm.out[1])) ? a.x1 : a.x2;
     }
     for (int i = gt; i < n; i += nt) a.out[i] = res[i];
@@ -1298,7 +1454,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_intersect(const IntersectArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    pipeline_init(sm);
+    pipeline_init(sm, a.S);
     Interval I = box_ball(a.S, sm, a.n, a.z, a.d, 1.0, a.lb, a.ub, a.has_box,
                           a.radius, a.line);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1320,7 +1476,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_matvec(const MatvecArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    pipeline_init(sm);
+    pipeline_init(sm, a.S);
     double a0 = 0.0, a1 = 0.0;
     if (a.kind == 0) spmv(a.M, a.x, epi_plain(a.y), sm, a.S, a0, a1);
     else hess_apply(a.H, a.S, a.x, a.y, nullptr, sm, a0);

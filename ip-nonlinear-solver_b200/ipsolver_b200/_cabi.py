@@ -94,6 +94,13 @@ PROTOTYPES = {
     "ipb_box_sphere_intersections": (C.c_int, [_P, _I64, _D, _D, _D, _D,
                                                C.c_double, C.c_int, _D, _D,
                                                C.POINTER(C.c_int)]),
+    "ipb_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_I64), C.POINTER(_I64),
+                                C.POINTER(_I64), C.POINTER(_I64), _I64, _I64, _P]),
+    "ipb_comm_connect": (C.c_int, [_P, _P]),
+    "ipb_comm_set_send_list": (C.c_int, [_P, C.c_int, _I64, _P]),
+    "ipb_csr_set_space": (C.c_int, [_P, _P, C.c_int]),
+    "ipb_proj_create_parts": (C.c_int, [_P, _P, _P, _P, _P, _P, _D, C.c_double, C.c_double,
+                                        C.c_int, C.c_double, C.c_int, C.POINTER(_P)]),
     "ipb_vec_create": (C.c_int, [_P, _I64, C.POINTER(_P)]),
     "ipb_vec_destroy": (C.c_int, [_P, _P]),
     "ipb_vec_upload": (C.c_int, [_P, _P, _D]),

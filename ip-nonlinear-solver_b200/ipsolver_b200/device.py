@@ -106,13 +106,17 @@ class DeviceVector:
 class DeviceCSR:
     """A scipy CSR matrix resident in HBM (values fp64, indices int32)."""
 
-    def __init__(self, ctx, M, with_transpose=True):
+    def __init__(self, ctx, M, with_transpose=True, local_columns=False, cols=None):
+        """``local_columns``: the column indices are a rank's local numbering
+        (own block at 0, ghost entries negative / past the own length; see
+        ``distributed.py``) and are taken as they are; ``cols`` is then the
+        own length of the column space."""
         M = sps.csr_matrix(M)
-        if not M.has_canonical_format:
+        if not local_columns and not M.has_canonical_format:
             M = M.copy()
             M.sum_duplicates()
         self.ctx = ctx
-        self.shape = M.shape
+        self.shape = M.shape if cols is None else (M.shape[0], int(cols))
         self.nnz = int(M.nnz)
         self.with_transpose = bool(with_transpose)
         indptr, indices = M.indptr, M.indices
@@ -125,7 +129,7 @@ class DeviceCSR:
         data = f64(M.data)
         h = C.c_void_p()
         ctx.check(ctx.lib.ipb_csr_create(
-            ctx.h, M.shape[0], M.shape[1], self.nnz,
+            ctx.h, self.shape[0], self.shape[1], self.nnz,
             indptr.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p),
             indptr.dtype.itemsize, dptr(data), int(with_transpose), C.byref(h)))
         self.h = h
@@ -335,6 +339,7 @@ def projected_cg_dev(proj, H, c, b, x, trust_radius=np.inf, lb=None, ub=None,
         -1 if max_iter is None else int(max_iter),
         -1 if max_infeasible_iter is None else int(max_infeasible_iter),
         x.h, C.byref(info))
+    proj.last_pcg_info = info
     ctx.check(st)
     return info
 

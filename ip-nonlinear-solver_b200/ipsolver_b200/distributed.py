@@ -1,0 +1,268 @@
+"""Row-partitioned multi-GPU runs of the hot path (one process per GPU).
+
+The reference is single-process; this is the B200-side
+extension ``north_star`` asks for.  Rank ``g`` owns a
+contiguous block of variables ``[n_off[g], n_off[g+1])`` -- all n-vectors, the
+rows of ``H`` and of ``A'`` -- and of constraints ``[m_off[g], m_off[g+1])`` --
+all m-vectors, the rows of ``A`` and of ``M = A~ A~'``.
+
+Pure numpy/scipy part (testable without a GPU):
+  :class:`RowPartition`  block offsets
+  :func:`local_parts`    this rank's matrices in local column numbering and
+                         the ghost entries they address
+  :func:`send_lists`     who pushes what to whom before a product
+
+Device part: :class:`DistSolver` sets up the symmetric arena, exchanges the
+CUDA-IPC handles through ``torch.distributed`` (plumbing only) and runs the
+same persistent kernels; inside them ghost entries are pushed over NVLink peer
+memory and reductions go through peer mailboxes (``csrc/device.cuh``,
+``halo_sync`` / ``rank_exchange``).
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sps
+
+N_SPACE, M_SPACE = 0, 1
+
+
+class RowPartition:
+    """Contiguous block partition of n variables and m constraints."""
+
+    def __init__(self, n, m, size):
+        self.n, self.m, self.size = int(n), int(m), int(size)
+        # variable blocks start on even indices (16-byte alignment of slices)
+        self.n_off = np.array([(g * self.n // size) & ~1 for g in range(size)] + [self.n],
+                              dtype=np.int64)
+        self.m_off = np.array([g * self.m // size for g in range(size)] + [self.m],
+                              dtype=np.int64)
+
+    def offsets(self, space):
+        return self.n_off if space == N_SPACE else self.m_off
+
+    def own(self, rank, space):
+        off = self.offsets(space)
+        return int(off[rank]), int(off[rank + 1])
+
+    def own_len(self, rank, space):
+        a, b = self.own(rank, space)
+        return b - a
+
+    def own_max(self, space):
+        return int(np.diff(self.offsets(space)).max())
+
+    def owner(self, idx, space):
+        return np.searchsorted(self.offsets(space), idx, side='right') - 1
+
+
+def _remote_columns(M, lo, hi):
+    """Sorted distinct column indices of M outside [lo, hi)."""
+    c = M.indices
+    c = c[(c < lo) | (c >= hi)]
+    return np.unique(c)
+
+
+def _localize(M, lo, hi, ghosts_lo, ghosts_hi):
+    """Renumber the columns of M: own ``c -> c - lo``; ghosts below / above
+    the own block go to ``-len(ghosts_lo) + position`` / ``own + position``."""
+    M = sps.csr_matrix(M)
+    c = M.indices.astype(np.int64)
+    out = c - lo
+    below, above = c < lo, c >= hi
+    if below.any():
+        out[below] = np.searchsorted(ghosts_lo, c[below]) - len(ghosts_lo)
+    if above.any():
+        out[above] = (hi - lo) + np.searchsorted(ghosts_hi, c[above])
+    L = sps.csr_matrix((M.data, out.astype(np.int32), M.indptr), shape=M.shape, copy=False)
+    return L
+
+
+def local_parts(part, rank, H, A):
+    """This rank's pieces of the QP matrices, in local column numbering.
+
+    ``H`` (n x n) and ``A`` (m x n) are the global scipy matrices (every rank
+    holds them -- fine up to n ~ 1e7; generating per partition is the next
+    step for config 5).  Returns a dict with CSR matrices ``H``, ``A_raw``,
+    ``A_norm``, ``At_raw``, ``At_norm``, ``M`` whose column indices are
+    relative to the rank's own block, the per-space ghost index lists
+    (global indices, ascending, split below / above the own block), the
+    row scaling of the own rows and ``||A||_F``."""
+    H = sps.csr_matrix(H)
+    A = sps.csr_matrix(A)
+    n0, n1 = part.own(rank, N_SPACE)
+    m0, m1 = part.own(rank, M_SPACE)
+    row_norm2 = np.asarray(A.multiply(A).sum(axis=1)).ravel()
+    dscale = np.where(row_norm2 > 0, 1.0 / np.sqrt(np.where(row_norm2 > 0, row_norm2, 1.0)), 0.0)
+    fro = float(np.sqrt(row_norm2.sum()))
+    An = sps.diags(dscale) @ A                       # row-normalised A
+    An = sps.csr_matrix(An)
+    An.sort_indices()
+    A_rows, An_rows = A[m0:m1], An[m0:m1]
+    At = sps.csr_matrix(A.T)
+    At.sort_indices()
+    Ant = sps.csr_matrix(An.T)
+    Ant.sort_indices()
+    At_rows, Ant_rows = At[n0:n1], Ant[n0:n1]
+    M_rows = sps.csr_matrix(An_rows @ An.T)          # own rows of A~ A~'
+    M_rows.sort_indices()
+    H_rows = H[n0:n1]
+    # ghost entries per space: union over the matrices whose columns live there
+    gn = np.union1d(_remote_columns(H_rows, n0, n1), _remote_columns(A_rows, n0, n1))
+    gm = np.union1d(_remote_columns(At_rows, m0, m1), _remote_columns(M_rows, m0, m1))
+    ghosts = {N_SPACE: (gn[gn < n0], gn[gn >= n1]), M_SPACE: (gm[gm < m0], gm[gm >= m1])}
+    loc_n = lambda X: _localize(X, n0, n1, *ghosts[N_SPACE])      # noqa: E731
+    loc_m = lambda X: _localize(X, m0, m1, *ghosts[M_SPACE])      # noqa: E731
+    return {
+        "H": loc_n(H_rows), "A_raw": loc_n(A_rows), "A_norm": loc_n(An_rows),
+        "At_raw": loc_m(At_rows), "At_norm": loc_m(Ant_rows), "M": loc_m(M_rows),
+        "ghosts": ghosts, "dscale": dscale[m0:m1].copy(), "fro": fro,
+        "own": {N_SPACE: (n0, n1), M_SPACE: (m0, m1)},
+    }
+
+
+def send_lists(part, rank, all_ghosts):
+    """``all_ghosts[g][space] = (below, above)`` of every rank ``g`` (global
+    indices).  Returns per space an ``(count, 4) int32`` array of
+    ``{own index, peer, index on the peer (own-relative), 0}``: what this rank
+    pushes before a product whose input lives in that space."""
+    out = {}
+    for space in (N_SPACE, M_SPACE):
+        lo, hi = part.own(rank, space)
+        ents = []
+        for g in range(part.size):
+            if g == rank:
+                continue
+            below, above = all_ghosts[g][space]
+            own_g = part.own_len(g, space)
+            for arr, base in ((below, -len(below)), (above, own_g)):
+                arr = np.asarray(arr, dtype=np.int64)
+                sel = np.nonzero((arr >= lo) & (arr < hi))[0]
+                if sel.size:
+                    e = np.zeros((sel.size, 4), dtype=np.int32)
+                    e[:, 0] = arr[sel] - lo
+                    e[:, 1] = g
+                    e[:, 2] = base + sel
+                    ents.append(e)
+        out[space] = (np.vstack(ents) if ents else np.zeros((0, 4), dtype=np.int32))
+    return out
+
+
+def ghost_capacity(all_ghosts, size):
+    """Symmetric ghost-zone sizes: maxima over the ranks (ghost_lo even)."""
+    glo, ghi = [0, 0], [0, 0]
+    for g in range(size):
+        for space in (N_SPACE, M_SPACE):
+            below, above = all_ghosts[g][space]
+            glo[space] = max(glo[space], len(below))
+            ghi[space] = max(ghi[space], len(above))
+    glo = [(x + 1) & ~1 for x in glo]
+    return glo, ghi
+
+
+def apply_local(L, x_own, ghosts_values_lo, ghosts_values_hi):
+    """Host model of a distributed product: ``L`` has local column numbering;
+    negative / beyond-own columns index the ghost values (used by the CPU
+    tests to check the partitioning against the global product)."""
+    own = len(x_own)
+    ext = np.concatenate([ghosts_values_lo, x_own, ghosts_values_hi])
+    shift = len(ghosts_values_lo)
+    E = sps.csr_matrix((L.data, L.indices.astype(np.int64) + shift, L.indptr),
+                       shape=(L.shape[0], own + shift + len(ghosts_values_hi)))
+    return E.dot(ext)
+
+
+# ---------------------------------------------------------------------------
+# device side
+# ---------------------------------------------------------------------------
+class DistSolver:
+    """One rank of a row-partitioned projected-CG solve.
+
+    ``group`` is a ``torch.distributed`` process group able to move Python
+    objects (gloo); it is used ONLY for setup (IPC handles, ghost lists) and
+    for max-over-ranks timing -- the data path inside the kernels is NVLink
+    peer memory, no NCCL call.
+    """
+
+    def __init__(self, H, A, rank, size, group=None, device=None, inner_rtol=1e-13,
+                 inner_maxit=1000, orth_tol=1e-12, max_refin=3, explicit_aat=True):
+        import torch.distributed as dist
+        from . import device as dev
+        self.rank, self.size = int(rank), int(size)
+        n, m = H.shape[0], A.shape[0]
+        self.part = RowPartition(n, m, size)
+        parts = local_parts(self.part, rank, H, A)
+        self.parts = parts
+        all_ghosts = [None] * size
+        dist.all_gather_object(all_ghosts, parts["ghosts"], group=group)
+        sends = send_lists(self.part, rank, all_ghosts)
+        glo, ghi = ghost_capacity(all_ghosts, size)
+        self.ctx = ctx = dev.Context(device)
+        lib = ctx.lib
+        I64x2 = C.c_int64 * 2
+        own = I64x2(self.part.own_len(rank, 0), self.part.own_len(rank, 1))
+        own_max = I64x2(self.part.own_max(0), self.part.own_max(1))
+        stride = [glo[k] + own_max[k] + ghi[k] + 64 for k in (0, 1)]
+        arena = 8 * (24 * stride[0] + 16 * stride[1]) + (1 << 20)
+        handle = (C.c_char * 64)()
+        ctx.check(lib.ipb_comm_init(ctx.h, self.rank, self.size, own, own_max, I64x2(*glo),
+                                    I64x2(*ghi), n - m, arena, handle))
+        handles = [None] * size
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        buf = (C.c_char * (64 * size)).from_buffer_copy(b"".join(handles))
+        dist.barrier(group=group)
+        ctx.check(lib.ipb_comm_connect(ctx.h, buf))
+        for space in (N_SPACE, M_SPACE):
+            e = np.ascontiguousarray(sends[space], dtype=np.int32)
+            ctx.check(lib.ipb_comm_set_send_list(ctx.h, space, e.shape[0],
+                                                 e.ctypes.data_as(C.c_void_p)))
+        self.n_own, self.m_own = own[0], own[1]
+        mk = lambda M_, space: self._csr(M_, space)        # noqa: E731
+        self.A_raw, self.A_norm = mk(parts["A_raw"], 0), mk(parts["A_norm"], 0)
+        self.At_raw, self.At_norm = mk(parts["At_raw"], 1), mk(parts["At_norm"], 1)
+        self.M = mk(parts["M"], 1) if explicit_aat else None
+        self.Hcsr = mk(parts["H"], 0)
+        self.H = dev.DeviceHessian(ctx, self.n_own, self.n_own, csr=self.Hcsr)
+        ph = C.c_void_p()
+        ds = np.ascontiguousarray(parts["dscale"], dtype=np.float64)
+        ctx.check(lib.ipb_proj_create_parts(
+            ctx.h, self.A_raw.h, self.A_norm.h, self.At_raw.h, self.At_norm.h,
+            self.M.h if self.M is not None else None, ds.ctypes.data_as(C.POINTER(C.c_double)),
+            parts["fro"], float(orth_tol), int(max_refin), float(inner_rtol), int(inner_maxit),
+            C.byref(ph)))
+        self.proj = _ProjHandle(ctx, ph, self.m_own, self.n_own)
+        dist.barrier(group=group)
+        self.group = group
+
+    def _csr(self, M_, space):
+        from . import device as dev
+        cols = self.n_own if space == N_SPACE else self.m_own
+        d = dev.DeviceCSR(self.ctx, M_, with_transpose=False, local_columns=True, cols=cols)
+        self.ctx.check(self.ctx.lib.ipb_csr_set_space(self.ctx.h, d.h, space))
+        return d
+
+    def local(self, v, space):
+        a, b = self.part.own(self.rank, space)
+        return np.ascontiguousarray(v[a:b], dtype=np.float64)
+
+    def vector(self, data=None, space=N_SPACE):
+        from . import device as dev
+        length = self.n_own if space == N_SPACE else self.m_own
+        return dev.DeviceVector(self.ctx, data=data, length=None if data is not None else length)
+
+    def projected_cg(self, c, b, x, **kw):
+        """``c``, ``b``, ``x``: DeviceVectors holding this rank's blocks."""
+        from . import device as dev
+        return dev.projected_cg_dev(self.proj, self.H, c, b, x, **kw)
+
+    def gather(self, x_local, space=N_SPACE):
+        import torch.distributed as dist
+        pieces = [None] * self.size
+        dist.all_gather_object(pieces, np.asarray(x_local), group=self.group)
+        return np.concatenate(pieces)
+
+
+class _ProjHandle:
+    """Minimal projector object for the *_dev calls (holds ctx and handle)."""
+
+    def __init__(self, ctx, h, m, n):
+        self.ctx, self.h, self.m, self.n = ctx, h, m, n

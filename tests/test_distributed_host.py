@@ -1,0 +1,129 @@
+"""Host logic of the row-partitioned multi-GPU path, on the CPU: the block
+partition, local column numbering, ghost lists and send lists reproduce the
+global products exactly; a world_size-2 gloo run exercises the collective
+plumbing (``all_gather_object`` of ghost lists) the device layer uses."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from ipsolver_b200 import synthetic
+from ipsolver_b200 import distributed as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def simulate(H, A, size, x_n, y_m):
+    """Run every rank's local products on the host, with ghost values moved by
+    the send lists exactly as the kernels move them; compare with global."""
+    n, m = H.shape[0], A.shape[0]
+    part = D.RowPartition(n, m, size)
+    parts = [D.local_parts(part, g, H, A) for g in range(size)]
+    all_ghosts = [p["ghosts"] for p in parts]
+    glo, ghi = D.ghost_capacity(all_ghosts, size)
+    sends = [D.send_lists(part, g, all_ghosts) for g in range(size)]
+    vec = {0: x_n, 1: y_m}
+    # extended local vectors [ghost_lo capacity | own | ghost_hi capacity], NaN-filled ghosts
+    ext = {}
+    for g in range(size):
+        for sp in (0, 1):
+            a, b = part.own(g, sp)
+            e = np.full(glo[sp] + (b - a) + ghi[sp], np.nan)
+            e[glo[sp]:glo[sp] + (b - a)] = vec[sp][a:b]
+            ext[g, sp] = e
+    for g in range(size):                 # the push: owner writes into the peer's ghost zone
+        for sp in (0, 1):
+            for src, peer, dst, _ in sends[g][sp]:
+                ext[peer, sp][glo[sp] + dst] = ext[g, sp][glo[sp] + src]
+    An = sps.diags(1.0 / np.sqrt(np.asarray(A.multiply(A).sum(axis=1)).ravel())) @ A
+    want = {"H": H.dot(x_n), "A_raw": A.dot(x_n), "A_norm": An.dot(x_n),
+            "At_raw": A.T.dot(y_m), "At_norm": An.T.dot(y_m), "M": (An @ An.T).dot(y_m)}
+    space = {"H": 0, "A_raw": 0, "A_norm": 0, "At_raw": 1, "At_norm": 1, "M": 1}
+    rows = {"H": 0, "A_raw": 1, "A_norm": 1, "At_raw": 0, "At_norm": 0, "M": 1}
+    for name in want:
+        got = []
+        for g in range(size):
+            L = parts[g][name]
+            sp = space[name]
+            a, b = part.own(g, sp)
+            e = ext[g, sp]
+            idx = L.indices.astype(np.int64) + glo[sp]
+            assert idx.min(initial=0) >= 0 and idx.max(initial=0) < e.shape[0]
+            E = sps.csr_matrix((L.data, idx, L.indptr), shape=(L.shape[0], e.shape[0]))
+            used = np.unique(idx)
+            assert not np.isnan(e[used]).any(), "a ghost entry was never pushed"
+            got.append(E.dot(np.nan_to_num(e)))
+        got = np.concatenate(got)
+        ra, rb = 0, (H.shape[0] if rows[name] == 0 else A.shape[0])
+        assert got.shape[0] == rb - ra
+        np.testing.assert_allclose(got, want[name], rtol=1e-13, atol=1e-13)
+    return part, parts, sends
+
+
+@pytest.mark.parametrize("pattern", ["window", "rand"])
+@pytest.mark.parametrize("size", [1, 2, 3, 8])
+def test_partitioned_products_match_global(pattern, size):
+    n = 4000
+    H, A, c, b = synthetic.make_qp(n, pattern, 1e3, seed=0)
+    part, parts, sends = simulate(H, A, size, c, b)
+    assert part.n_off[0] == 0 and part.n_off[-1] == n and (part.n_off[:-1] % 2 == 0).all()
+    if pattern == "window" and size > 1:
+        # halo of a windowed matrix is a handful of entries per neighbour
+        assert max(len(s[0]) for s in sends) <= 64
+        for p in parts:
+            assert len(p["ghosts"][0][0]) <= 32 and len(p["ghosts"][0][1]) <= 32
+
+
+def test_ragged_partition_more_ranks_than_rows():
+    H, A, c, b = synthetic.make_qp(12, "window", 10.0, seed=0)
+    simulate(H, A, 8, c, b)
+
+
+WORKER = r'''
+import os, sys, numpy as np
+sys.path[:0] = [%r, %r]
+import torch.distributed as dist
+from ipsolver_b200 import synthetic, distributed as D
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% sys.argv[1],
+                        rank=int(sys.argv[2]), world_size=2)
+rank = dist.get_rank()
+H, A, c, b = synthetic.make_qp(2000, "window", 1e3, seed=0)
+part = D.RowPartition(2000, 1000, 2)
+p = D.local_parts(part, rank, H, A)
+allg = [None, None]
+dist.all_gather_object(allg, p["ghosts"])
+sends = D.send_lists(part, rank, allg)
+# every ghost my peer holds that I own is in my send list, once
+peer = 1 - rank
+for sp in (0, 1):
+    lo, hi = part.own(rank, sp)
+    want = sum(int(((g >= lo) & (g < hi)).sum()) for g in allg[peer][sp])
+    assert sends[sp].shape[0] == want, (sends[sp].shape, want)
+    assert (sends[sp][:, 1] == peer).all()
+# the local product with ghosts fetched from the peer equals the global one
+x_parts = [None, None]
+dist.all_gather_object(x_parts, c[part.own(rank, 0)[0]:part.own(rank, 0)[1]])
+x = np.concatenate(x_parts)
+glo_v, ghi_v = x[p["ghosts"][0][0]], x[p["ghosts"][0][1]]
+y = D.apply_local(p["A_raw"], x_parts[rank], glo_v, ghi_v)
+m0, m1 = part.own(rank, 1)
+assert np.allclose(y, A.dot(c)[m0:m1], rtol=1e-13, atol=1e-13)
+dist.barrier()
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % (ROOT, os.path.join(ROOT, "ip-nonlinear-solver_b200")))
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), port, str(r)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert "rank %d ok" % r in o
