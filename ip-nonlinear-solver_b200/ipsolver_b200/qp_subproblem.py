@@ -57,6 +57,19 @@ class HessianOperator(LinearOperator):
         self._ctx = ctx
         self._dev = None
 
+    def with_diag_tail(self, diag_tail):
+        """``blockdiag(self, diag(diag_tail))`` -- the scaled barrier Hessian
+        (``tr_interior_point.py:222-241``); the matrix terms are shared."""
+        if self.diag_tail is not None:
+            raise ValueError("operator already has a diagonal tail")
+        out = HessianOperator.__new__(HessianOperator)
+        out.diag_tail = f64(diag_tail)
+        out.n_x = self.n
+        out.n = self.n + out.diag_tail.shape[0]
+        LinearOperator.__init__(out, dtype=np.float64, shape=(out.n, out.n))
+        out.sparse, out.dense, out._ctx, out._dev = self.sparse, self.dense, self._ctx, None
+        return out
+
     @property
     def device(self):
         if self._dev is None:

@@ -1,0 +1,95 @@
+"""Host logic of the outer loops (``ipsolver_b200.equality_constrained_sqp``,
+``tr_interior_point``, ``minimize_constrained``) on the CPU: driven with the
+ORACLE's hot-path routines (test-only ``hot_path`` injection) they must
+reproduce the reference's end-to-end results -- the golden vectors in
+``tests/golden/e2e.npz`` were produced by the unmodified reference
+(``tests/golden/make_golden.py``).  Iteration counts must match exactly here:
+the oracle is bit-identical to the reference's linear algebra, so any
+difference would be in the outer-loop restatement."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+from scipy.sparse.linalg import LinearOperator
+
+import oracle
+import e2e_problems
+import ipsolver_b200 as ipb
+
+
+class HostHessian(LinearOperator):
+    """What the reference's closures compute (_canonical_constraint.py:119-139,
+    tr_interior_point.py:222-241): the products of the terms added up one
+    after the other, and the diagonal slack block."""
+
+    def __init__(self, n, terms, diag_tail=None):
+        self.terms, self.diag_tail = list(terms), diag_tail
+        self.n_x = n
+        n_all = n + (0 if diag_tail is None else len(diag_tail))
+        super().__init__(dtype=np.float64, shape=(n_all, n_all))
+
+    def with_diag_tail(self, tail):
+        return HostHessian(self.n_x, self.terms, np.asarray(tail, dtype=float))
+
+    def _matvec(self, p):
+        p = np.asarray(p, dtype=float).ravel()
+        px = p[:self.n_x]
+        out = np.zeros_like(px)
+        for h in self.terms:
+            out += h.dot(px)
+        if self.diag_tail is None:
+            return out
+        return np.hstack((out, self.diag_tail * p[self.n_x:]))
+
+
+ORACLE_PATH = SimpleNamespace(
+    projections=lambda A, method=None: oracle.build_projectors(A, method),
+    projected_cg=oracle.eqp_projected_cg,
+    modified_dogleg=oracle.dogleg_normal_step,
+    box_intersections=oracle.segment_box,
+    hessian=HostHessian)
+
+
+def run(name):
+    api = dict(minimize_constrained=lambda *a, **k: ipb.minimize_constrained(
+                   *a, hot_path=ORACLE_PATH, **k),
+               LinearConstraint=ipb.LinearConstraint, BoxConstraint=ipb.BoxConstraint,
+               NonlinearConstraint=ipb.NonlinearConstraint)
+    return e2e_problems.PROBLEMS[name](api)()
+
+
+@pytest.mark.parametrize("name", ["eqp_window_2000", "eqp_rand_2000", "eqp_window_2000_gtol6",
+                                  "ipqp_window_1000", "thomson_20_equals", "thomson_20_less"])
+def test_outer_loop_reproduces_reference(golden_dir, name):
+    import os
+    gold = np.load(os.path.join(golden_dir, "e2e.npz"))
+    niter, cg, status, nfev, opt, viol, fval, radius = gold[name + "/scalars"]
+    res = run(name)
+    assert (res.niter, res.cg_niter, res.status, res.nfev) == (niter, cg, status, nfev)
+    np.testing.assert_allclose(res.x, gold[name + "/x"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(res.v, gold[name + "/v"], rtol=1e-9, atol=1e-12)
+    assert res.fun == pytest.approx(fval, rel=1e-13)
+    assert res.trust_radius == pytest.approx(radius, rel=1e-12)
+
+
+def test_kind_vocabulary_and_row_order():
+    from ipsolver_b200.minimize_constrained import _Rows
+    x0 = np.array([1.0, 2.0, 3.0, 4.0])
+    r = _Rows(lambda x: x, lambda x: np.eye(4), None,
+              ("interval", [0, -np.inf, 3, -1], [2, 5, 3, np.inf]), False, x0, None)
+    assert list(r.eq) == [2] and list(r.val_eq) == [3.0]
+    # lower-bound rows first, then upper-bound rows (reference _parse_constraint)
+    assert list(r.ineq) == [0, 3, 0, 1]
+    assert list(r.sign) == [-1, -1, 1, 1]
+    c_in, c_eq = r.values(x0)
+    assert list(c_in) == [-1.0, -5.0, -1.0, -3.0] and list(c_eq) == [0.0]
+    with pytest.raises(ValueError):
+        _Rows(lambda x: x, lambda x: np.eye(4), None, ("between", 0, 1), False, x0, None)
+    with pytest.raises(ValueError):
+        _Rows(lambda x: x, lambda x: np.eye(4), None, ("interval", 0), False, x0, None)
+
+
+def test_fd_hessian_is_rejected():
+    with pytest.raises(TypeError):
+        ipb.minimize_constrained(lambda x: x.dot(x), np.ones(3), lambda x: 2 * x, '2-point',
+                                 hot_path=ORACLE_PATH)
