@@ -165,6 +165,29 @@ def cpu_reference_run(n, iters, steps, warmup, pattern, kappa):
     return done / dt, dt, t_factor
 
 
+def solve_problem(n, pattern="window", kappa=10.0):
+    """BASELINE config 2: convex equality-constrained QP through
+    ``minimize_constrained(..., method='equality_constrained_sqp')``."""
+    from ipsolver_b200 import synthetic
+    H, A, q, b = synthetic.make_qp(n, pattern, kappa, seed=0)
+    args = (lambda x: 0.5 * x.dot(H.dot(x)) + q.dot(x), np.zeros(n),
+            lambda x: H.dot(x) + q, lambda x: H)
+    return args, A, b
+
+
+def end_to_end_solve(n, hot_path=None):
+    import ipsolver_b200 as ipb
+    args, A, b = solve_problem(n)
+    t0 = time.perf_counter()
+    res = ipb.minimize_constrained(*args, ipb.LinearConstraint(A, ("equals", b)),
+                                   method='equality_constrained_sqp', hot_path=hot_path)
+    dt = time.perf_counter() - t0
+    return {"n": n, "m": n // 2, "seconds": dt, "niter": int(res.niter),
+            "cg_niter": int(res.cg_niter), "status": int(res.status),
+            "optimality": float(res.optimality),
+            "constr_violation": float(res.constr_violation)}
+
+
 def run_reference(args):
     """--impl reference: the CPU path on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -348,6 +371,17 @@ def run_b200(args):
                                        t_factor, scale),
                "measured_it_per_s_at_sample": its, "host_cpus": os.cpu_count()}
 
+    # ---- end-to-end solve (BASELINE config 2: n = 1e6 through the SQP outer loop)
+    solve = None
+    if args.solve_n > 0:
+        solve = {"b200": end_to_end_solve(args.solve_n),
+                 "what": "minimize_constrained(method='equality_constrained_sqp') on the "
+                         "synthetic convex QP, outer loop on the host, every linear-algebra "
+                         "step on the device"}
+        if not args.no_cpu and args.solve_cpu_n > 0:
+            import oracle
+            solve["cpu_oracle"] = end_to_end_solve(args.solve_cpu_n, oracle.host_hot_path())
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup,
@@ -357,6 +391,7 @@ def run_b200(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "setup_s": {"generate": t_gen, "upload_and_transpose": t_setup},
+        "end_to_end_solve": solve,
         "grid": dict(zip(("blocks", "threads", "sms"), ctx.grid())),
         "e2e_vs_resident_rel_diff": same,
     }
@@ -509,6 +544,10 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=1_000_000)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--solve-n", type=int, default=1_000_000,
+                    help="size of the end-to-end SQP solve (0: skip)")
+    ap.add_argument("--solve-cpu-n", type=int, default=100_000,
+                    help="size of the same solve on the CPU oracle (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

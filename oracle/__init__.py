@@ -22,5 +22,5 @@ is pinned against the mathematically identical ``AugmentedSystem`` projector
 from .refpath import (  # noqa: F401
     segment_ball, segment_box, segment_box_ball, in_box, clip_to_box,
     dogleg_normal_step, eqp_projected_cg, kkt_direct_solve,
-    orthogonality_measure, build_projectors,
+    orthogonality_measure, build_projectors, HostLagrangianHessian, host_hot_path,
 )

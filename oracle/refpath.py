@@ -447,3 +447,43 @@ def build_projectors(A, method=None, orth_tol=1e-12, max_refin=3, tol=1e-15,
     LS = spla.LinearOperator((m, n), least_squares)
     Y = spla.LinearOperator((n, m), row_space)
     return Z, LS, Y
+
+
+# --------------------------------------------------------------------------
+# host model of the Lagrangian Hessian operators and the whole hot-path bundle
+# --------------------------------------------------------------------------
+class HostLagrangianHessian(spla.LinearOperator):
+    """What the reference's Hessian closures compute
+    (``ipsolver/_canonical_constraint.py:119-139``: the products of the terms
+    added up one after the other; ``tr_interior_point.py:222-241``: plus the
+    diagonal slack block)."""
+
+    def __init__(self, n, terms, diag_tail=None):
+        self.terms, self.diag_tail = list(terms), diag_tail
+        self.n_x = n
+        n_all = n + (0 if diag_tail is None else len(diag_tail))
+        super().__init__(dtype=np.float64, shape=(n_all, n_all))
+
+    def with_diag_tail(self, tail):
+        return HostLagrangianHessian(self.n_x, self.terms, np.asarray(tail, dtype=float))
+
+    def _matvec(self, p):
+        p = np.asarray(p, dtype=float).ravel()
+        px = p[:self.n_x]
+        out = np.zeros_like(px)
+        for h in self.terms:
+            out += h.dot(px)
+        if self.diag_tail is None:
+            return out
+        return np.hstack((out, self.diag_tail * p[self.n_x:]))
+
+
+def host_hot_path():
+    """The oracle's routines bundled the way the outer loops of
+    ``ipsolver_b200`` take them (``hot_path=``): used by the CPU tests and by
+    the CPU-baseline legs of ``bench.py`` only."""
+    from types import SimpleNamespace
+    return SimpleNamespace(
+        projections=lambda A, method=None: build_projectors(A, method),
+        projected_cg=eqp_projected_cg, modified_dogleg=dogleg_normal_step,
+        box_intersections=segment_box, hessian=HostLagrangianHessian)

@@ -6,48 +6,15 @@ reproduce the reference's end-to-end results -- the golden vectors in
 (``tests/golden/make_golden.py``).  Iteration counts must match exactly here:
 the oracle is bit-identical to the reference's linear algebra, so any
 difference would be in the outer-loop restatement."""
-from types import SimpleNamespace
-
 import numpy as np
 import pytest
-from scipy.sparse.linalg import LinearOperator
 
 import oracle
 import e2e_problems
 import ipsolver_b200 as ipb
 
 
-class HostHessian(LinearOperator):
-    """What the reference's closures compute (_canonical_constraint.py:119-139,
-    tr_interior_point.py:222-241): the products of the terms added up one
-    after the other, and the diagonal slack block."""
-
-    def __init__(self, n, terms, diag_tail=None):
-        self.terms, self.diag_tail = list(terms), diag_tail
-        self.n_x = n
-        n_all = n + (0 if diag_tail is None else len(diag_tail))
-        super().__init__(dtype=np.float64, shape=(n_all, n_all))
-
-    def with_diag_tail(self, tail):
-        return HostHessian(self.n_x, self.terms, np.asarray(tail, dtype=float))
-
-    def _matvec(self, p):
-        p = np.asarray(p, dtype=float).ravel()
-        px = p[:self.n_x]
-        out = np.zeros_like(px)
-        for h in self.terms:
-            out += h.dot(px)
-        if self.diag_tail is None:
-            return out
-        return np.hstack((out, self.diag_tail * p[self.n_x:]))
-
-
-ORACLE_PATH = SimpleNamespace(
-    projections=lambda A, method=None: oracle.build_projectors(A, method),
-    projected_cg=oracle.eqp_projected_cg,
-    modified_dogleg=oracle.dogleg_normal_step,
-    box_intersections=oracle.segment_box,
-    hessian=HostHessian)
+ORACLE_PATH = oracle.host_hot_path()
 
 
 def run(name):
