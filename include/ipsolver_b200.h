@@ -235,6 +235,13 @@ int ipb_vec_download(ipb_ctx *ctx, const ipb_vec *v, double *host);
 int64_t ipb_vec_len(const ipb_vec *v);
 void *ipb_vec_ptr(ipb_vec *v);   /* raw device pointer (for torch interop) */
 
+/* ---- pinned host memory --------------------------------------------------- */
+/* Page-locked buffers for results: the host mirror hands large outputs (x of
+ * projected_cg, projector results) back in such buffers, so the device-to-host
+ * copy runs at PCIe rate instead of through a pageable bounce. */
+int ipb_host_alloc(ipb_ctx *ctx, int64_t bytes, void **out);
+int ipb_host_free(ipb_ctx *ctx, void *p);
+
 /* ---- measurement helpers (bench.py) -------------------------------------- */
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of
  * this library is launched on; torch.cuda.Event would not see it). */

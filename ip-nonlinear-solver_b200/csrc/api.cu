@@ -821,7 +821,7 @@ extern "C" int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int ma
     p->orth_tol = orth_tol; p->max_refin = max_refin;
     p->rtol = inner_rtol > 0 ? inner_rtol : 1e-13;
     p->maxit = inner_maxit > 0 ? inner_maxit : 1000;
-    size_t m = A->rows, n = A->cols, nnz = A->nnz;
+    size_t m = A->rows, nnz = A->nnz;
     CHECK(dalloc(ctx, &p->nval, nnz + PAD));
     CHECK(dalloc(ctx, &p->nt_val, nnz + PAD));
     CHECK(dalloc(ctx, &p->dscale, m));
@@ -1174,6 +1174,19 @@ extern "C" int ipb_box_sphere_intersections(ipb_ctx *ctx, int64_t n, const doubl
     CU(ctx, cudaMemcpyAsync(h, ctx->d_result, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     *ta = h->ta; *tb = h->tb; *intersect = h->hit;
+    return IPB_OK;
+}
+
+// ------------------------------------------------------------------ pinned host memory
+extern "C" int ipb_host_alloc(ipb_ctx *ctx, int64_t bytes, void **out) {
+    if (!ctx || !out || bytes < 0) return IPB_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 8)));
+    return IPB_OK;
+}
+extern "C" int ipb_host_free(ipb_ctx *ctx, void *p) {
+    (void)ctx;
+    if (p) cudaFreeHost(p);
     return IPB_OK;
 }
 

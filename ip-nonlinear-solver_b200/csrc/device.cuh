@@ -680,6 +680,103 @@ __device__ __forceinline__ void set_ops(Smem &sm, int o0, int o1 = 0, int o2 = 0
     __syncthreads();
 }
 
+// ---------------------------------------------------------------- fused CG update
+// p = r + beta p;  s = w + beta s;  v += alpha p;  r -= alpha s;  returns this
+// thread's share of r.r -- the one vector pass of the inner iteration
+// (5 reads + 4 writes of m-vectors).  It runs as a TMA pipeline through the
+// same shared-memory stages as the SpMV: tiles of UT entries of the five
+// vectors come in by bulk copies, are updated in place in shared memory and
+// go out by bulk stores (cp.async.bulk.global.shared::cta), so the pass does
+// not depend on L1 (almost none is left next to the stages) and keeps deep
+// queues of reads and writes in flight.
+constexpr int UT = (int)((sizeof(Stage) / (5 * sizeof(double))) & ~(size_t)31);
+
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"(smem_addr(src)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void update_issue(const ProjView &P, Smem &sm, int s, int t0, int cnt) {
+    double *buf = reinterpret_cast<double *>(&sm.st[s]);
+    const unsigned bytes = (unsigned)(((cnt + 1) & ~1) * 8);
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(smem_addr(&sm.full[s])), "r"(5u * bytes) : "memory");
+    bulk_g2s(buf + 0 * UT, P.r + t0, bytes, &sm.full[s]);
+    bulk_g2s(buf + 1 * UT, P.w + t0, bytes, &sm.full[s]);
+    bulk_g2s(buf + 2 * UT, P.p + t0, bytes, &sm.full[s]);
+    bulk_g2s(buf + 3 * UT, P.s + t0, bytes, &sm.full[s]);
+    bulk_g2s(buf + 4 * UT, P.v + t0, bytes, &sm.full[s]);
+}
+
+__device__ __noinline__ double cg_update(const ProjView &P, Smem &sm, const SyncView &S,
+                                         double alpha, double beta) {
+    const int tid = threadIdx.x;
+    const int m = P.m;
+    double gpart = 0.0;
+    __syncthreads();
+    const int ntile = (m + UT - 1) / UT;
+    const int per = (ntile + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int first = (int)blockIdx.x * per;
+    const int nmine = min(per, ntile - first);
+    if (nmine <= 0) return 0.0;
+    const unsigned base = sm.seq;
+    if (tid == 0)
+        for (int k = 0; k < NSTAGE && k < nmine; ++k) {
+            const int t0 = (first + k) * UT;
+            update_issue(P, sm, (base + k) % NSTAGE, t0, min(UT, m - t0));
+        }
+    for (int j = 0; j < nmine; ++j) {
+        const unsigned u = base + j;
+        const int s = u % NSTAGE;
+        const int t0 = (first + j) * UT;
+        const int cnt = min(UT, m - t0);
+        double *buf = reinterpret_cast<double *>(&sm.st[s]);
+        mbar_wait(&sm.full[s], (u / NSTAGE) & 1u, S.abort_flag);
+        for (int e = tid; e < cnt; e += THREADS) {
+            const double ri = buf[e], wi = buf[UT + e];
+            const double pi = ri + beta * buf[2 * UT + e];
+            const double si = wi + beta * buf[3 * UT + e];
+            const double vi = buf[4 * UT + e] + alpha * pi;
+            const double rn = ri - alpha * si;
+            buf[2 * UT + e] = pi; buf[3 * UT + e] = si; buf[4 * UT + e] = vi; buf[e] = rn;
+            gpart += rn * rn;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            // never write past the own range (the next entry may be a ghost a
+            // peer has just pushed): an odd last entry goes out by plain stores
+            const unsigned bytes = (unsigned)((cnt & ~1) * 8);
+            if (bytes) {
+                bulk_s2g(P.r + t0, buf, bytes);
+                bulk_s2g(P.p + t0, buf + 2 * UT, bytes);
+                bulk_s2g(P.s + t0, buf + 3 * UT, bytes);
+                bulk_s2g(P.v + t0, buf + 4 * UT, bytes);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (cnt & 1) {
+                const int e = cnt - 1;
+                P.r[t0 + e] = buf[e]; P.p[t0 + e] = buf[2 * UT + e];
+                P.s[t0 + e] = buf[3 * UT + e]; P.v[t0 + e] = buf[4 * UT + e];
+            }
+            if (j + NSTAGE < nmine) {
+                // the stores must have read the stage before it is refilled
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                const int n0 = (first + j + NSTAGE) * UT;
+                update_issue(P, sm, s, n0, min(UT, m - n0));
+            }
+        }
+    }
+    if (tid == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // writes complete
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        sm.seq = base + (unsigned)nmine;
+    }
+    __syncthreads();
+    return gpart;
+}
+
 // ---------------------------------------------------------------- inner CG
 // w = (A~ A~') r with  acc0 += w.r : one SpMV with the explicit product M
 // when the projector holds it (half the matrix bytes and no n-vector
@@ -739,39 +836,7 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
     int k = 0;
     while (k < maxit) {
         ++k;
-        gpart = 0.0;
-        {
-            // fused 4-vector update, 128-bit accesses, two in flight per thread
-            const int m2 = m >> 1;
-            double2 *r2 = reinterpret_cast<double2 *>(P.r);
-            double2 *p2 = reinterpret_cast<double2 *>(P.p);
-            double2 *s2 = reinterpret_cast<double2 *>(P.s);
-            double2 *v2 = reinterpret_cast<double2 *>(P.v);
-            const double2 *w2 = reinterpret_cast<const double2 *>(P.w);
-#pragma unroll 2
-            for (int i = gt; i < m2; i += nt) {
-                double2 ri = ld_stream2(r2 + i), wi = ld_stream2(w2 + i), pi = ld_stream2(p2 + i),
-                        si = ld_stream2(s2 + i), vi = ld_stream2(v2 + i);
-                pi.x = ri.x + beta * pi.x; pi.y = ri.y + beta * pi.y;
-                si.x = wi.x + beta * si.x; si.y = wi.y + beta * si.y;
-                vi.x = vi.x + alpha * pi.x; vi.y = vi.y + alpha * pi.y;
-                ri.x = ri.x - alpha * si.x; ri.y = ri.y - alpha * si.y;
-                st_stream2(p2 + i, pi); st_stream2(s2 + i, si); st_stream2(v2 + i, vi); st_stream2(r2 + i, ri);
-                gpart += ri.x * ri.x;
-                gpart += ri.y * ri.y;
-            }
-            if ((m & 1) && gt == 0) {
-                const int i = m - 1;
-                double ri = P.r[i], wi = P.w[i];
-                double pi = ri + beta * P.p[i];
-                double si = wi + beta * P.s[i];
-                P.p[i] = pi; P.s[i] = si;
-                P.v[i] = P.v[i] + alpha * pi;
-                ri = ri - alpha * si;
-                P.r[i] = ri;
-                gpart += ri * ri;
-            }
-        }
+        gpart = cg_update(P, sm, S, alpha, beta);
         grid_sync(S);
         a0 = 0.0;
         normal_apply(P, S, sm, a0);
@@ -1273,28 +1338,10 @@ k_projector(const ProjArgs a) {
     } else if (a.op >= 10) {
         // one phase of the inner iteration repeated fixed_iters times, each
         // followed by a grid barrier (measurement only; results discarded)
-        const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
         double a0 = 0.0, a1 = 0.0;
         for (int it = 0; it < a.fixed_iters; ++it) {
             if (a.op == 10) {
-                const int m2 = P.m >> 1;
-                double2 *r2 = reinterpret_cast<double2 *>(P.r);
-                double2 *p2 = reinterpret_cast<double2 *>(P.p);
-                double2 *s2 = reinterpret_cast<double2 *>(P.s);
-                double2 *v2 = reinterpret_cast<double2 *>(P.v);
-                const double2 *w2 = reinterpret_cast<const double2 *>(P.w);
-                const double alpha = 1e-3, beta = 0.5;
-#pragma unroll 2
-                for (int i = gt; i < m2; i += nt) {
-                    double2 ri = ld_stream2(r2 + i), wi = ld_stream2(w2 + i), pi = ld_stream2(p2 + i),
-                        si = ld_stream2(s2 + i), vi = ld_stream2(v2 + i);
-                    pi.x = ri.x + beta * pi.x; pi.y = ri.y + beta * pi.y;
-                    si.x = wi.x + beta * si.x; si.y = wi.y + beta * si.y;
-                    vi.x = vi.x + alpha * pi.x; vi.y = vi.y + alpha * pi.y;
-                    ri.x = ri.x - alpha * si.x; ri.y = ri.y - alpha * si.y;
-                    st_stream2(p2 + i, pi); st_stream2(s2 + i, si); st_stream2(v2 + i, vi); st_stream2(r2 + i, ri);
-                    a1 += ri.x * ri.x + ri.y * ri.y;
-                }
+                a1 += cg_update(P, sm, S, 1e-3, 0.5);
             } else if (a.op == 11) {
                 spmv(P.At, P.r, epi_plain(P.t), sm, S, a0, a1);
             } else if (a.op == 12) {

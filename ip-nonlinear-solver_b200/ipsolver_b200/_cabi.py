@@ -107,6 +107,8 @@ PROTOTYPES = {
     "ipb_vec_download": (C.c_int, [_P, _P, _D]),
     "ipb_vec_len": (_I64, [_P]),
     "ipb_vec_ptr": (_P, [_P]),
+    "ipb_host_alloc": (C.c_int, [_P, _I64, C.POINTER(_P)]),
+    "ipb_host_free": (C.c_int, [_P, _P]),
     "ipb_timer_start": (C.c_int, [_P]),
     "ipb_timer_stop": (C.c_int, [_P, _D]),
     "ipb_bench_inner_iterations": (C.c_int, [_P, _P, _P, C.c_int, _D]),

@@ -43,6 +43,34 @@ class Context:
             cls._default = cls()
         return cls._default
 
+    # ---- pinned result buffers, recycled when the numpy array is collected
+    PIN_MIN = 1 << 15          # doubles; smaller results use ordinary numpy memory
+
+    def empty(self, n):
+        """Uninitialised float64 array of length n for a device result: page-locked
+        (recycled through a per-context pool) when large."""
+        n = int(n)
+        if n < self.PIN_MIN:
+            return np.empty(n)
+        pool = self.__dict__.setdefault("_pin_pool", {})
+        free = pool.setdefault(n, [])
+        if free:
+            ptr = free.pop()
+        else:
+            p = C.c_void_p()
+            self.check(self.lib.ipb_host_alloc(self.h, 8 * n, C.byref(p)))
+            ptr = p.value
+        arr = np.ctypeslib.as_array((C.c_double * n).from_address(ptr))
+        weakref.finalize(arr, self._unpin, ptr, n)
+        return arr
+
+    def _unpin(self, ptr, n):
+        free = self._pin_pool.setdefault(n, [])
+        if len(free) < 4:
+            free.append(ptr)
+        else:
+            self.lib.ipb_host_free(self.h, C.c_void_p(ptr))
+
     def check(self, st):
         if st == 0:
             return
@@ -249,7 +277,7 @@ class DeviceProjector:
 
     def null_space(self, x):
         x = f64(x, self.n)
-        z = np.empty(self.n)
+        z = self.ctx.empty(self.n)
         info = ProjInfo()
         self.ctx.check(self.ctx.lib.ipb_proj_null_space(
             self.ctx.h, self.h, dptr(x), dptr(z), C.byref(info)))
@@ -258,7 +286,7 @@ class DeviceProjector:
 
     def least_squares(self, x):
         x = f64(x, self.n)
-        v = np.empty(self.m)
+        v = self.ctx.empty(self.m)
         info = ProjInfo()
         self.ctx.check(self.ctx.lib.ipb_proj_least_squares(
             self.ctx.h, self.h, dptr(x), dptr(v), C.byref(info)))
@@ -267,7 +295,7 @@ class DeviceProjector:
 
     def row_space(self, b):
         b = f64(b, self.m)
-        y = np.empty(self.n)
+        y = self.ctx.empty(self.n)
         info = ProjInfo()
         self.ctx.check(self.ctx.lib.ipb_proj_row_space(
             self.ctx.h, self.h, dptr(b), dptr(y), C.byref(info)))
@@ -283,7 +311,7 @@ class DeviceProjector:
     def modified_dogleg(self, b, trust_radius, lb=None, ub=None):
         b = f64(b, self.m)
         lb, ub = _bounds(lb, ub, self.n)
-        x = np.empty(self.n)
+        x = self.ctx.empty(self.n)
         info = ProjInfo()
         self.ctx.check(self.ctx.lib.ipb_modified_dogleg(
             self.ctx.h, self.h, dptr(b), float(trust_radius), dptr(lb), dptr(ub),
@@ -297,7 +325,7 @@ class DeviceProjector:
         c = f64(c, self.n)
         b = f64(b, self.m)
         lb, ub = _bounds(lb, ub, self.n)
-        x = np.empty(self.n)
+        x = self.ctx.empty(self.n)
         info = PcgInfo()
         cap = 0
         allvecs = None
