@@ -201,20 +201,26 @@ int ipb_box_sphere_intersections(ipb_ctx *ctx, int64_t n, const double *z,
  * solver vectors of a rank live in a symmetric arena laid out
  * [ghost_lo | own | ghost_hi], matrices are given per rank with column indices
  * relative to the own block (negative / past the end = ghost entries).  Inside
- * the kernels the owners push ghost entries to their peers over NVLink peer
- * memory before each product, and reductions go through per-rank mailboxes in
- * peer memory, summed in rank order (bit-identical on all ranks).
+ * the kernels the owners send ghost entries into their peers' ghost mailboxes
+ * over NVLink peer memory before each product (no barrier between the ranks:
+ * only the row blocks that read ghosts wait for them), and reductions go
+ * through per-rank mailboxes in peer memory, summed in rank order
+ * (bit-identical on all ranks).
  *   own / own_max / ghost_lo / ghost_hi : 2 entries each, [0] n-space, [1] m-space
  *     (own: this rank's block length; own_max, ghost_*: maxima over the ranks,
- *     identical on all ranks; ghost_lo even)
+ *     identical on all ranks; ghost_lo even; my_ghost_*: the entries this rank
+ *     really holds below / above its own block)
  *   n_minus_m_global : n - m of the whole problem (iteration cap, qp_subproblem.py:537)
  *   ipc_handle_out   : 64 bytes to be all-gathered and passed to ipb_comm_connect
  * Host-vector entry points are single-GPU; partitioned runs use *_dev calls. */
 int ipb_comm_init(ipb_ctx *ctx, int rank, int size, const int64_t *own,
                   const int64_t *own_max, const int64_t *ghost_lo, const int64_t *ghost_hi,
+                  const int64_t *my_ghost_lo, const int64_t *my_ghost_hi,
                   int64_t n_minus_m_global, int64_t arena_bytes, void *ipc_handle_out);
 int ipb_comm_connect(ipb_ctx *ctx, const void *handles /* size x 64 bytes, rank order */);
-/* entries: count x {own index, peer rank, index on the peer (own-relative), 0} (int32) */
+/* entries: count x {own index, peer rank, index on the peer (own-relative), slot in the
+ * peer's ghost mailbox = ghost_lo capacity + that index if it is negative, else ghost_lo
+ * capacity + (index - the peer's own length)} (int32) */
 int ipb_comm_set_send_list(ipb_ctx *ctx, int space, int64_t count, const int32_t *entries);
 /* vector space of a matrix's columns (0: n-space, 1: m-space) -- selects the halo list */
 int ipb_csr_set_space(ipb_ctx *ctx, ipb_csr *m, int space);

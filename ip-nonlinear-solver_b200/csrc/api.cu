@@ -94,6 +94,8 @@ struct ipb_ctx {
     size_t arena_bytes = 0, arena_used = 0, arena_vec0 = 0;
     char *peer_base[MAX_RANKS] = {nullptr};
     int64_t own[2] = {0, 0}, own_max[2] = {0, 0}, glo[2] = {0, 0}, ghi[2] = {0, 0};
+    int64_t n_lo[2] = {0, 0}, n_hi[2] = {0, 0};       // ghost entries this rank really holds
+    size_t gmbox_off[2] = {0, 0};                      // ghost mailboxes inside the arena
     int4 *send_ent[2] = {nullptr, nullptr};
     int send_cnt[2] = {0, 0};
     int64_t nm_global = -1;
@@ -102,7 +104,8 @@ struct ipb_ctx {
 };
 
 static const size_t MBOX_BYTES = 4 * MAX_RANKS * NSLOT * 2 * sizeof(unsigned long long);
-static const size_t FLAG_OFF = MBOX_BYTES, SEQ_OFF = FLAG_OFF + 256, VEC_OFF = SEQ_OFF + 256;
+static const size_t FLAG_OFF = MBOX_BYTES, SEQ_OFF = FLAG_OFF + 256, GFLAG_OFF = SEQ_OFF + 256,
+                    VEC_OFF = GFLAG_OFF + 256;
 
 #define IPB_FAIL(ctx, code, ...)                                              \
     do {                                                                      \
@@ -159,7 +162,16 @@ static SyncView sync_view(const ipb_ctx *ctx) {
             s.C.peer_mbox[q] = (double *)ctx->peer_base[q];
             s.C.peer_flag[q] = (unsigned *)(ctx->peer_base[q] + FLAG_OFF);
         }
-        for (int k = 0; k < 2; ++k) { s.C.send[k].ent = ctx->send_ent[k]; s.C.send[k].count = ctx->send_cnt[k]; }
+        s.C.ghost_flag = (unsigned *)(ctx->arena + GFLAG_OFF);
+        for (int k = 0; k < 2; ++k) {
+            s.C.send[k].ent = ctx->send_ent[k]; s.C.send[k].count = ctx->send_cnt[k];
+            s.C.gmbox[k] = (unsigned long long *)(ctx->arena + ctx->gmbox_off[k]);
+            for (int q = 0; q < ctx->size; ++q)
+                s.C.peer_gmbox[k][q] = (unsigned long long *)(ctx->peer_base[q] + ctx->gmbox_off[k]);
+            s.C.gcap[k] = (int)(ctx->glo[k] + ctx->ghi[k]); s.C.gcap_lo[k] = (int)ctx->glo[k];
+            s.C.n_lo[k] = (int)ctx->n_lo[k]; s.C.n_hi[k] = (int)ctx->n_hi[k];
+            s.C.own_len[k] = (int)ctx->own[k];
+        }
     }
     return s;
 }
@@ -205,7 +217,7 @@ static CsrView csr_view_t(const ipb_csr *m, const double *val_override = nullptr
 // Cut the rows of a CSR matrix into blocks of at most CHUNK nnz and RMAX rows
 // (greedy, in row order); a row longer than CHUNK becomes a block of its own.
 // rowptr is read back from the device (once per sparsity pattern).
-static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, const int *d_col, int rows,
+static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, const int *d_col, int rows, int cols,
                         int4 **d_desc, int *nblk);
 
 // number of CTAs for a launch working on ``work`` items: enough to fill the
@@ -215,7 +227,7 @@ static int grid_for(const ipb_ctx *ctx, int64_t work) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(ctx->blocks, want));
 }
 
-static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, const int *d_col, int rows,
+static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, const int *d_col, int rows, int cols,
                         int4 **d_desc, int *nblk) {
     std::vector<int> rp((size_t)rows + 1);
     CU(ctx, cudaMemcpyAsync(rp.data(), d_rowptr, ((size_t)rows + 1) * sizeof(int),
@@ -243,7 +255,7 @@ static int build_blocks(ipb_ctx *ctx, const int *d_rowptr, const int *d_col, int
     if (!desc.empty()) {
         CU(ctx, cudaMemcpyAsync(*d_desc, desc.data(), desc.size() * sizeof(int4),
                                 cudaMemcpyHostToDevice, ctx->stream));
-        k_block_colrange<<<cdiv((int64_t)*nblk * 32, 256), 256, 0, ctx->stream>>>(*nblk, *d_desc, d_col);
+        k_block_colrange<<<cdiv((int64_t)*nblk * 32, 256), 256, 0, ctx->stream>>>(*nblk, *d_desc, d_col, cols);
         ctx->launches += 1;
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -463,7 +475,7 @@ static int build_transpose(ipb_ctx *ctx, ipb_csr *m) {
                                               m->cols + 1, ctx->stream));
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CHECK(build_blocks(ctx, m->t_rowptr, m->t_col, m->cols, &m->t_desc, &m->t_nblk));
+    CHECK(build_blocks(ctx, m->t_rowptr, m->t_col, m->cols, m->rows, &m->t_desc, &m->t_nblk));
     m->has_t = true;
     return IPB_OK;
 }
@@ -504,7 +516,7 @@ extern "C" int ipb_csr_create(ipb_ctx *ctx, int64_t rows, int64_t cols, int64_t 
     if (nnz) CU(ctx, cudaMemcpyAsync(m->val, data, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (rows == 0) CU(ctx, cudaMemsetAsync(m->rowptr, 0, sizeof(int), ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if ((s = build_blocks(ctx, m->rowptr, m->col, m->rows, &m->desc, &m->nblk)) != IPB_OK) return s;
+    if ((s = build_blocks(ctx, m->rowptr, m->col, m->rows, m->cols, &m->desc, &m->nblk)) != IPB_OK) return s;
     if (with_transpose) {
         s = build_transpose(ctx, m);
         if (s != IPB_OK) return s;
@@ -765,7 +777,7 @@ static int build_aat_pattern(ipb_ctx *ctx, ipb_proj *p) {
             cudaError_t e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); status = IPB_ERR_CUDA; }
             if (status == IPB_OK)
-                status = build_blocks(ctx, p->m_rowptr, p->m_col, m, &p->m_desc, &p->m_nblk);
+                status = build_blocks(ctx, p->m_rowptr, p->m_col, m, m, &p->m_desc, &p->m_nblk);
             if (status == IPB_OK) p->has_M = true;
         }
         if (status != IPB_OK) free_aat(p);
@@ -1199,10 +1211,11 @@ extern "C" int ipb_csr_set_space(ipb_ctx *ctx, ipb_csr *m, int space) {
 
 extern "C" int ipb_comm_init(ipb_ctx *ctx, int rank, int size, const int64_t *own,
                              const int64_t *own_max, const int64_t *ghost_lo,
-                             const int64_t *ghost_hi, int64_t n_minus_m_global,
+                             const int64_t *ghost_hi, const int64_t *my_ghost_lo,
+                             const int64_t *my_ghost_hi, int64_t n_minus_m_global,
                              int64_t arena_bytes, void *ipc_handle_out) {
     if (!ctx || size < 1 || size > MAX_RANKS || rank < 0 || rank >= size || !own || !own_max ||
-        !ghost_lo || !ghost_hi || !ipc_handle_out)
+        !ghost_lo || !ghost_hi || !my_ghost_lo || !my_ghost_hi || !ipc_handle_out)
         return IPB_ERR_INVALID;
     if (ctx->arena) IPB_FAIL(ctx, IPB_ERR_INVALID, "ipb_comm_init called twice");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1210,12 +1223,21 @@ extern "C" int ipb_comm_init(ipb_ctx *ctx, int rank, int size, const int64_t *ow
         if (ghost_lo[k] & 1) IPB_FAIL(ctx, IPB_ERR_INVALID, "ghost_lo must be even (16-byte alignment)");
         ctx->own[k] = own[k]; ctx->own_max[k] = own_max[k];
         ctx->glo[k] = ghost_lo[k]; ctx->ghi[k] = ghost_hi[k];
+        if (my_ghost_lo[k] > ghost_lo[k] || my_ghost_hi[k] > ghost_hi[k])
+            IPB_FAIL(ctx, IPB_ERR_INVALID, "a rank's ghost count exceeds the common capacity");
+        ctx->n_lo[k] = my_ghost_lo[k]; ctx->n_hi[k] = my_ghost_hi[k];
     }
     ctx->rank = rank; ctx->size = size; ctx->nm_global = n_minus_m_global;
-    ctx->arena_bytes = ((size_t)arena_bytes + VEC_OFF + 4095) & ~(size_t)4095;
+    // ghost mailboxes: 4 generations x capacity x 2 words, per space (same offsets on every rank)
+    size_t off = VEC_OFF;
+    for (int k = 0; k < 2; ++k) {
+        ctx->gmbox_off[k] = off;
+        off += ((size_t)4 * (size_t)(ghost_lo[k] + ghost_hi[k]) * 16 + 255) & ~(size_t)255;
+    }
+    ctx->arena_bytes = ((size_t)arena_bytes + off + 4095) & ~(size_t)4095;
     CU(ctx, cudaMalloc((void **)&ctx->arena, ctx->arena_bytes));
     CU(ctx, cudaMemset(ctx->arena, 0, ctx->arena_bytes));
-    ctx->arena_used = VEC_OFF;
+    ctx->arena_used = off;
     cudaIpcMemHandle_t h;
     CU(ctx, cudaIpcGetMemHandle(&h, ctx->arena));
     memcpy(ipc_handle_out, &h, sizeof h);

@@ -88,7 +88,7 @@ constexpr int MAX_RANKS = 8;
 //   * reductions: every rank posts its partial sums into every peer's mailbox
 //     and adds the mailbox up in rank order -- bit-identical on all ranks.
 struct SendList {
-    const int4 *ent;          // {src index (own), peer, dst index on the peer (own-relative), 0}
+    const int4 *ent;          // {src index (own), peer, dst index on the peer (own-relative), mailbox slot}
     int count;
 };
 struct CommView {
@@ -101,6 +101,13 @@ struct CommView {
     unsigned *peer_flag[MAX_RANKS];
     unsigned *seq;            // sequence counter of this rank (persists across launches)
     SendList send[2];         // 0: n-space vectors, 1: m-space vectors
+    // ghost mailboxes ("LL": 2 words {sequence, 32 bits} per entry, 4 generations)
+    unsigned long long *gmbox[2];                  // this rank's, per space
+    unsigned long long *peer_gmbox[2][MAX_RANKS];
+    int gcap[2], gcap_lo[2];  // slots per generation; slots below gcap_lo are ghost_lo entries
+    int n_lo[2], n_hi[2];     // ghost entries this rank really holds
+    int own_len[2];
+    unsigned *ghost_flag;     // [2] local: sequence number of the last ghost zone filled
 };
 
 struct SyncView {
@@ -254,6 +261,7 @@ struct __align__(128) Smem {
     unsigned done[NSTAGE];        // warps that have finished with the stage's block
     unsigned seq;                 // stage uses of this CTA so far (slot = seq % NSTAGE)
     unsigned gseq;                // cross-GPU sequence number (multi-GPU only)
+    unsigned ghost_seq;           // sequence number the ghost zone of the current product carries
     double red[WARPS];
     double out[NSLOT];
     int ops[NSLOT];
@@ -361,28 +369,6 @@ __device__ __forceinline__ void rank_allreduce(const SyncView &S, Smem &sm, int 
     __syncthreads();
 }
 
-// Flag barrier across the ranks, with release/acquire semantics for the
-// remote stores (ghost pushes) that CTA 0 -- or, after a grid barrier, the
-// whole grid -- made before it: CTA 0 posts this sequence number into every
-// peer's flag array, every CTA waits for every rank's number.
-__device__ __forceinline__ void rank_barrier(const SyncView &S, Smem &sm) {
-    const CommView &C = S.C;
-    const unsigned seq = sm.gseq + 1u;
-    if (blockIdx.x == 0) {
-        __threadfence_system();
-        __syncthreads();
-        if ((int)threadIdx.x < C.size) st_release_sys(C.peer_flag[threadIdx.x] + C.rank, seq);
-        if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned *>(C.seq) = seq;
-    }
-    if ((int)threadIdx.x < C.size) {
-        long long spins = 0;
-        while ((int)(ld_acquire_sys(C.flag + threadIdx.x) - seq) < 0)
-            if (++spins > (1ll << 28)) { *S.abort_flag = 3; __trap(); }
-    }
-    if (threadIdx.x == 0) sm.gseq = seq;
-    __syncthreads();
-}
-
 // After a grid_sync: sm.out[slot] = combination of every CTA's (and every
 // rank's) partial of slots [0, nslots), in a fixed order -- bit-identical in
 // every thread of every rank.
@@ -391,30 +377,90 @@ __device__ __forceinline__ void collect(const SyncView &S, Smem &sm, int nslots)
     if (S.C.size > 1) rank_allreduce(S, sm, nslots);
 }
 
-// Called with x final on every rank (the condition any SpMV needs anyway):
-// push the entries of x that peers hold as ghosts, then meet.  Short lists
-// are pushed by CTA 0 alone (one grid barrier less).
+// Ghost exchange before a product, called by ALL CTAs with x final on this
+// rank (the condition any SpMV needs anyway).  No barrier between the ranks:
+//   * the COMMUNICATOR CTA (the last one; it takes no row blocks) sends the
+//     entries its peers hold as ghosts into their ghost mailboxes, LL style
+//     -- {sequence number, 32 bits} words that are their own arrival flag,
+//     one NVLink hop, no fence -- then polls its own mailbox for the entries
+//     this rank needs, writes them into x's ghost zone and releases the local
+//     flag ghost_flag[space] = sequence number;
+//   * every other CTA starts its blocks at once; only a block whose columns
+//     reach into a ghost zone (descriptor flag) waits for that flag, and the
+//     CTA that owns block 0 walks its range backwards so that this block
+//     comes last -- the exchange hides behind the interior blocks.
+// Long lists (random sparsity) are sent and received by all CTAs, followed by
+// a grid barrier.  Mailbox generation = seq & 3; the ghost zone itself is only
+// ever written by its own rank, so a fast peer cannot overwrite values in use.
+__device__ __forceinline__ void ll_store(unsigned long long *dst, unsigned seq, double v) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long lo = ((unsigned long long)seq << 32) | (bits & 0xffffffffull);
+    const unsigned long long hi = ((unsigned long long)seq << 32) | (bits >> 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ double ll_wait(const unsigned long long *src, unsigned seq, int *abort_flag) {
+    unsigned long long lo, hi;
+    long long spins = 0;
+    do {
+        asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+        if (++spins > (1ll << 28)) { *abort_flag = 4; __trap(); }
+    } while ((unsigned)(lo >> 32) != seq || (unsigned)(hi >> 32) != seq);
+    return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+}
+
 __device__ __noinline__ void halo_sync(const SyncView &S, Smem &sm, const double *x, int space) {
     const CommView &C = S.C;
     const SendList L = C.send[space];
-    const ptrdiff_t off = x - C.arena;                 // same offset on every rank
-    const bool small = L.count <= 4 * THREADS;
-    if (small) {
-        if (blockIdx.x == 0)
-            for (int i = threadIdx.x; i < L.count; i += THREADS) {
-                const int4 e = __ldg(L.ent + i);
-                C.peer_arena[e.y][off + e.z] = x[e.x];
-            }
-    } else {
-        const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
-        for (int i = gt; i < L.count; i += nt) {
-            const int4 e = __ldg(L.ent + i);
-            C.peer_arena[e.y][off + e.z] = x[e.x];
-        }
-        __threadfence_system();
-        grid_sync(S);
+    const unsigned seq = sm.gseq + 1u;
+    const int gen = (int)(seq & 3u);
+    const int cap = C.gcap[space], cap_lo = C.gcap_lo[space];
+    const int nl = C.n_lo[space], ng = nl + C.n_hi[space];
+    double *xw = const_cast<double *>(x);
+    const bool small = L.count <= 4 * THREADS && ng <= 4 * THREADS;
+    const bool comm = blockIdx.x == gridDim.x - 1;
+    int i0, istep;
+    if (small) { i0 = comm ? (int)threadIdx.x : 0x7fffffff; istep = THREADS; }
+    else { i0 = blockIdx.x * THREADS + threadIdx.x; istep = gridDim.x * THREADS; }
+    for (int i = i0; i < L.count; i += istep) {
+        const int4 e = __ldg(L.ent + i);
+        ll_store(C.peer_gmbox[space][e.y] + 2 * ((size_t)gen * cap + e.w), seq, x[e.x]);
     }
-    rank_barrier(S, sm);
+    for (int g = i0; g < ng; g += istep) {
+        const int slot = g < nl ? cap_lo - nl + g : cap_lo + (g - nl);
+        const double v = ll_wait(C.gmbox[space] + 2 * ((size_t)gen * cap + slot), seq, S.abort_flag);
+        xw[slot < cap_lo ? slot - cap_lo : C.own_len[space] + (slot - cap_lo)] = v;
+    }
+    if (small) {
+        if (comm) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                asm volatile("st.release.gpu.global.u32 [%0],%1;" ::"l"(C.ghost_flag + space), "r"(seq) : "memory");
+                *reinterpret_cast<volatile unsigned *>(C.seq) = seq;
+            }
+        }
+    } else {
+        __threadfence();
+        grid_sync(S);
+        if (comm && threadIdx.x == 0) {
+            asm volatile("st.release.gpu.global.u32 [%0],%1;" ::"l"(C.ghost_flag + space), "r"(seq) : "memory");
+            *reinterpret_cast<volatile unsigned *>(C.seq) = seq;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { sm.gseq = seq; sm.ghost_seq = seq; }
+    __syncthreads();
+}
+
+// A block that reads ghost entries may only be staged once they are in place.
+__device__ __forceinline__ void ghost_wait(const SyncView &S, const Smem &sm, int space) {
+    const unsigned want = sm.ghost_seq;
+    unsigned have;
+    long long spins = 0;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0,[%1];" : "=r"(have) : "l"(S.C.ghost_flag + space) : "memory");
+        if (++spins > (1ll << 28)) { *S.abort_flag = 5; __trap(); }
+    } while ((int)(have - want) < 0);
 }
 
 // ---------------------------------------------------------------- SpMV
@@ -454,11 +500,12 @@ __device__ __forceinline__ void row_out(const Epi &e, int r, double s, double ad
 // xcnt <= XMAX, or xcnt = 0 when the column span is too wide to stage.
 // Blocks are cut at upload so that len <= CHUNK and r1 - r0 <= RMAX; a row
 // longer than CHUNK is a block of its own (len > CHUNK).
-struct BlockDesc { int r0, r1, p0, len, c0, xcnt; };
+struct BlockDesc { int r0, r1, p0, len, c0, xcnt, ghost; };
 
 __device__ __forceinline__ BlockDesc load_desc(const int4 *desc, size_t blk) {
     const int4 a = __ldg(desc + 2 * blk), b = __ldg(desc + 2 * blk + 1);
     BlockDesc d; d.r0 = a.x; d.r1 = a.y; d.p0 = a.z; d.len = a.w; d.c0 = b.x; d.xcnt = b.y;
+    d.ghost = b.z;
     return d;
 }
 
@@ -545,21 +592,30 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
                                        double &acc1) {
     const int tid = threadIdx.x;
     __syncthreads();                       // sm.seq of the previous call is visible
-    const int per = (M.nblk + (int)gridDim.x - 1) / (int)gridDim.x;
+    // multi-GPU: the last CTA is the communicator (halo_sync) and takes no blocks
+    const bool dist = S.C.size > 1;
+    const int workers = (dist && gridDim.x > 1) ? (int)gridDim.x - 1 : (int)gridDim.x;
+    const int per = (M.nblk + workers - 1) / workers;
     const int first = (int)blockIdx.x * per;
-    const int nmine = min(per, M.nblk - first);
+    const int nmine = (int)blockIdx.x < workers ? min(per, M.nblk - first) : 0;
     if (nmine <= 0) return;
     const unsigned base = sm.seq;
+    // the CTA that owns block 0 (the one that reads ghost_lo) walks backwards
+    const bool rev = dist && first == 0;
     const int4 *dp = M.desc + 2 * (size_t)first;
+#define IPB_BLK(j) (rev ? nmine - 1 - (j) : (j))
     // x slices are staged only when the bulk-copy source is 16-byte aligned
     const bool xstage = (reinterpret_cast<size_t>(x) & 15) == 0;
     if (tid == 0)
-        for (int k = 0; k < NSTAGE && k < nmine; ++k)
-            stage_issue(M, load_desc(dp, k), x, xstage, sm, (base + k) % NSTAGE);
-    BlockDesc d = load_desc(dp, 0);
+        for (int k = 0; k < NSTAGE && k < nmine; ++k) {
+            const BlockDesc dk = load_desc(dp, IPB_BLK(k));
+            if (dist && dk.ghost) ghost_wait(S, sm, M.space);
+            stage_issue(M, dk, x, xstage, sm, (base + k) % NSTAGE);
+        }
+    BlockDesc d = load_desc(dp, IPB_BLK(0));
     for (int j = 0; j < nmine; ++j) {
-        const BlockDesc dnext = load_desc(dp, min(j + 1, nmine - 1));
-        const BlockDesc dfar = load_desc(dp, min(j + NSTAGE, nmine - 1));
+        const BlockDesc dnext = load_desc(dp, IPB_BLK(min(j + 1, nmine - 1)));
+        const BlockDesc dfar = load_desc(dp, IPB_BLK(min(j + NSTAGE, nmine - 1)));
         const unsigned u = base + j;
         const int s = u % NSTAGE;
         if (d.len <= CHUNK) {
@@ -592,11 +648,15 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
             if (old == WARPS - 1) {
                 atomicExch(&sm.done[s], 0u);
                 __threadfence_block();
-                if (j + NSTAGE < nmine) stage_issue(M, dfar, x, xstage, sm, s);
+                if (j + NSTAGE < nmine) {
+                    if (dist && dfar.ghost) ghost_wait(S, sm, M.space);
+                    stage_issue(M, dfar, x, xstage, sm, s);
+                }
             }
         }
         d = dnext;
     }
+#undef IPB_BLK
     __syncthreads();
     if (tid == 0) sm.seq = base + (unsigned)nmine;
 }
@@ -1645,16 +1705,15 @@ __global__ void k_aat_values(int rows, const int *rowptr, const int *col,
 }
 
 // column range of every row block -> {c0, xcnt} (second int4 of its descriptor)
-__global__ void k_block_colrange(int nblk, int4 *desc, const int *col) {
+__global__ void k_block_colrange(int nblk, int4 *desc, const int *col, int cols) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nblk) return;
     const int4 a = desc[2 * (size_t)warp];
-    int lo = 0x7fffffff, hi = -1;
-    if (a.w <= CHUNK)
-        for (int q = a.z + lane; q < a.z + a.w; q += 32) {
-            const int c = col[q];
-            lo = min(lo, c); hi = max(hi, c);
-        }
+    int lo = 0x7fffffff, hi = -0x7fffffff;
+    for (int q = a.z + lane; q < a.z + a.w; q += 32) {
+        const int c = col[q];
+        lo = min(lo, c); hi = max(hi, c);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -1662,12 +1721,14 @@ __global__ void k_block_colrange(int nblk, int4 *desc, const int *col) {
     }
     if (lane == 0) {
         int c0 = 0, xcnt = 0;
-        if (hi >= lo) {
+        if (hi >= lo && a.w <= CHUNK) {
             c0 = lo & ~1;
             xcnt = (hi - c0 + 2) & ~1;
             if (xcnt > XMAX) { c0 = 0; xcnt = 0; }
         }
-        desc[2 * (size_t)warp + 1] = make_int4(c0, xcnt, 0, 0);
+        // columns outside [0, cols) are ghost entries of a row-partitioned run
+        const int ghost = (hi >= lo && (lo < 0 || hi >= cols)) ? 1 : 0;
+        desc[2 * (size_t)warp + 1] = make_int4(c0, xcnt, ghost, 0);
     }
 }
 

@@ -95,7 +95,8 @@ PROTOTYPES = {
                                                C.c_double, C.c_int, _D, _D,
                                                C.POINTER(C.c_int)]),
     "ipb_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_I64), C.POINTER(_I64),
-                                C.POINTER(_I64), C.POINTER(_I64), _I64, _I64, _P]),
+                                C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64),
+                                C.POINTER(_I64), _I64, _I64, _P]),
     "ipb_comm_connect": (C.c_int, [_P, _P]),
     "ipb_comm_set_send_list": (C.c_int, [_P, C.c_int, _I64, _P]),
     "ipb_csr_set_space": (C.c_int, [_P, _P, C.c_int]),

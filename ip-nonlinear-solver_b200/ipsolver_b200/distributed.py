@@ -120,11 +120,16 @@ def local_parts(part, rank, H, A):
     }
 
 
-def send_lists(part, rank, all_ghosts):
+def send_lists(part, rank, all_ghosts, glo_cap=None):
     """``all_ghosts[g][space] = (below, above)`` of every rank ``g`` (global
     indices).  Returns per space an ``(count, 4) int32`` array of
-    ``{own index, peer, index on the peer (own-relative), 0}``: what this rank
-    pushes before a product whose input lives in that space."""
+    ``{own index, peer, index on the peer (own-relative), slot in the peer's
+    ghost mailbox}``: what this rank sends before a product whose input lives
+    in that space.  Mailbox slots: the peer's ghost_lo entries sit right below
+    ``glo_cap[space]`` (the common ghost_lo capacity), its ghost_hi entries
+    start at it."""
+    if glo_cap is None:
+        glo_cap = ghost_capacity(all_ghosts, part.size)[0]
     out = {}
     for space in (N_SPACE, M_SPACE):
         lo, hi = part.own(rank, space)
@@ -142,6 +147,7 @@ def send_lists(part, rank, all_ghosts):
                     e[:, 0] = arr[sel] - lo
                     e[:, 1] = g
                     e[:, 2] = base + sel
+                    e[:, 3] = glo_cap[space] + (base + sel if base < 0 else sel)
                     ents.append(e)
         out[space] = (np.vstack(ents) if ents else np.zeros((0, 4), dtype=np.int32))
     return out
@@ -194,8 +200,8 @@ class DistSolver:
         self.parts = parts
         all_ghosts = [None] * size
         dist.all_gather_object(all_ghosts, parts["ghosts"], group=group)
-        sends = send_lists(self.part, rank, all_ghosts)
         glo, ghi = ghost_capacity(all_ghosts, size)
+        sends = send_lists(self.part, rank, all_ghosts, glo)
         self.ctx = ctx = dev.Context(device)
         lib = ctx.lib
         I64x2 = C.c_int64 * 2
@@ -204,8 +210,10 @@ class DistSolver:
         stride = [glo[k] + own_max[k] + ghi[k] + 64 for k in (0, 1)]
         arena = 8 * (24 * stride[0] + 16 * stride[1]) + (1 << 20)
         handle = (C.c_char * 64)()
+        mine = parts["ghosts"]
         ctx.check(lib.ipb_comm_init(ctx.h, self.rank, self.size, own, own_max, I64x2(*glo),
-                                    I64x2(*ghi), n - m, arena, handle))
+                                    I64x2(*ghi), I64x2(len(mine[0][0]), len(mine[1][0])),
+                                    I64x2(len(mine[0][1]), len(mine[1][1])), n - m, arena, handle))
         handles = [None] * size
         dist.all_gather_object(handles, bytes(handle.raw), group=group)
         buf = (C.c_char * (64 * size)).from_buffer_copy(b"".join(handles))

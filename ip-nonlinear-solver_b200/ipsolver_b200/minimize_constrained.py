@@ -118,6 +118,9 @@ class _Rows:
     def jacobians(self, x):
         J = self.jac(x)
         n = J.shape[1]
+        if len(self.ineq) == 0 and len(self.eq) == self.m:
+            # every row is an equality row, in order: no row selection needed
+            return (sps.csr_matrix((0, n)) if self.sparse else np.empty((0, n))), J
         if self.sparse:
             J_eq = J[self.eq, :] if len(self.eq) else sps.csr_matrix((0, n))
             J_in = (sps.diags(self.sign) @ J[self.ineq, :]).tocsr() if len(self.ineq) \

@@ -13,7 +13,7 @@ import numpy as np
 import scipy.sparse as sps
 from scipy.sparse.linalg import LinearOperator
 
-from .device import Context, DeviceHessian, _bounds
+from .device import Context, DeviceCSR, DeviceHessian, _bounds
 from ._cabi import dptr, f64
 from .projections import DeviceMap
 
@@ -72,9 +72,26 @@ class HessianOperator(LinearOperator):
 
     @property
     def device(self):
+        """Device operator.  The CSR term is cached per sparsity pattern on the
+        context: a new Hessian with the pattern of the previous one (every outer
+        iteration of the SQP / barrier loops) only re-uploads its values instead
+        of rebuilding row blocks and descriptors."""
         if self._dev is None:
             ctx = self._ctx or Context.default()
-            self._dev = DeviceHessian(ctx, self.n, self.n_x, csr=self.sparse,
+            csr = None
+            if self.sparse is not None:
+                S = self.sparse
+                if not S.has_canonical_format:
+                    S = S.copy()
+                    S.sum_duplicates()
+                cache = ctx.__dict__.setdefault("_hess_csr_cache", {})
+                key = (S.shape, S.nnz)
+                csr = cache.get(key)
+                if csr is not None and csr.same_pattern(S):
+                    csr.update_values(S.data)
+                else:
+                    csr = cache[key] = DeviceCSR(ctx, S, with_transpose=False)
+            self._dev = DeviceHessian(ctx, self.n, self.n_x, csr=csr,
                                       dense=self.dense, diag_tail=self.diag_tail)
         return self._dev
 

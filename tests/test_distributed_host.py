@@ -36,7 +36,11 @@ def simulate(H, A, size, x_n, y_m):
             ext[g, sp] = e
     for g in range(size):                 # the push: owner writes into the peer's ghost zone
         for sp in (0, 1):
-            for src, peer, dst, _ in sends[g][sp]:
+            for src, peer, dst, slot in sends[g][sp]:
+                # the receiver derives the ghost index from the mailbox slot alone
+                own_peer = part.own_len(peer, sp)
+                assert (slot - glo[sp] if slot < glo[sp] else own_peer + slot - glo[sp]) == dst
+                assert 0 <= slot < glo[sp] + ghi[sp]
                 ext[peer, sp][glo[sp] + dst] = ext[g, sp][glo[sp] + src]
     An = sps.diags(1.0 / np.sqrt(np.asarray(A.multiply(A).sum(axis=1)).ravel())) @ A
     want = {"H": H.dot(x_n), "A_raw": A.dot(x_n), "A_norm": An.dot(x_n),
