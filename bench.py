@@ -416,7 +416,10 @@ def run_b200_dist(args):
         raise SystemExit("--gpus %d needs torchrun with %d ranks (WORLD_SIZE=%d)"
                          % (args.gpus, args.gpus, size))
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl")
+    # keep stdout for the one JSON line: NCCL and friends may print banners
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gloo = dist.new_group(backend="gloo")
     n, m = args.n, args.n // 2
     t0 = time.perf_counter()
@@ -525,7 +528,10 @@ def run_b200_dist(args):
             "setup_s": {"generate": t_gen, "partition_upload_connect": t_setup},
             "result_check": {"rel_feasibility": feas},
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     dist.barrier()
     dist.destroy_process_group()
 

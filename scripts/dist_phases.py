@@ -10,7 +10,7 @@ from ipsolver_b200 import synthetic, device, distributed as D  # noqa: E402
 rank = int(os.environ.get("RANK", "0")); size = int(os.environ.get("WORLD_SIZE", "1"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
-dist.init_process_group("nccl")
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 gloo = dist.new_group(backend="gloo")
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
 H, A, c, b = synthetic.make_qp(n, 'window', 1e4, 0)
