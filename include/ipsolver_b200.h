@@ -262,7 +262,8 @@ int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x,
 /* Repeats ONE phase of the inner iteration ``reps`` times inside one launch,
  * a grid barrier after each (0: fused vector update, 1: A' r, 2: A t, 3: M r,
  * 4: barrier only, 5: the bulk-copy pipeline of M r without the arithmetic,
- * 6: barrier + cross-GPU all-reduce, 7: barrier + ghost push of an m-vector);
+ * 6: barrier + cross-GPU all-reduce, 7: barrier + ghost push of an m-vector,
+ * 8: the row arithmetic of M r without the copy pipeline);
  * returns device milliseconds.  Results are discarded and
  * the projector's work vectors are overwritten. */
 int ipb_bench_phase(ipb_ctx *ctx, ipb_proj *p, int phase, int reps, double *ms);

@@ -992,7 +992,7 @@ extern "C" int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_v
 }
 
 extern "C" int ipb_bench_phase(ipb_ctx *ctx, ipb_proj *p, int phase, int reps, double *ms) {
-    if (!ctx || !p || reps <= 0 || phase < 0 || phase > 7) return IPB_ERR_INVALID;
+    if (!ctx || !p || reps <= 0 || phase < 0 || phase > 8) return IPB_ERR_INVALID;
     ipb_proj_info info;
     CHECK(run_proj(ctx, p, 10 + phase, p->rhs, nullptr, reps, &info));
     if (ms) *ms = info.kernel_ms;

@@ -606,6 +606,21 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
 #define IPB_BLK(j) (rev ? nmine - 1 - (j) : (j))
     // x slices are staged only when the bulk-copy source is 16-byte aligned
     const bool xstage = (reinterpret_cast<size_t>(x) & 15) == 0;
+    if (M.space == 2) {
+        // measurement only: the row arithmetic without the copy pipeline -- the
+        // CTA's first block is staged once and processed nmine times
+        const BlockDesc d0 = load_desc(dp, 0);
+        if (d0.len > CHUNK) return;
+        if (tid == 0) stage_issue(M, d0, x, xstage, sm, base % NSTAGE);
+        mbar_wait(&sm.full[base % NSTAGE], (base / NSTAGE) & 1u, S.abort_flag);
+        for (int j = 0; j < nmine; ++j) {
+            if (xstage && d0.xcnt > 0) block_rows<true, FAST>(sm.st[base % NSTAGE], d0, x, e, acc0, acc1);
+            else block_rows<false, FAST>(sm.st[base % NSTAGE], d0, x, e, acc0, acc1);
+        }
+        __syncthreads();
+        if (tid == 0) sm.seq = base + 1u;
+        return;
+    }
     if (tid == 0)
         for (int k = 0; k < NSTAGE && k < nmine; ++k) {
             const BlockDesc dk = load_desc(dp, IPB_BLK(k));
@@ -1412,6 +1427,10 @@ k_projector(const ProjArgs a) {
                 spmv(P.M, P.r, e, sm, S, a0, a1);
             } else if (a.op == 15 && P.has_M) {
                 spmv(P.M, P.r, epi_plain(nullptr), sm, S, a0, a1);   // bulk copies only
+            } else if (a.op == 18 && P.has_M) {
+                Epi e = epi_plain(P.w); e.dotv = P.r;
+                CsrView Mp = P.M; Mp.space = 2;                     // row arithmetic only
+                spmv(Mp, P.r, e, sm, S, a0, a1);
             } else if (a.op == 16) {
                 // a two-value reduction exactly as the solvers do it
                 publish(S, 0, 1.0, OP_SUM, sm.red);

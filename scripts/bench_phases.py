@@ -32,6 +32,7 @@ phases = [
     ("w = M r, w.r", 3, B(nnzM, m, m)),
     ("barrier only", 4, 0),
     ("M r copy pipeline only", 5, 12 * nnzM + 4 * (m + 1) + 8 * m),
+    ("M r row arithmetic only", 8, 0),
 ]
 import torch  # noqa: E402
 _a = torch.empty(1 << 27, dtype=torch.float64, device='cuda')
