@@ -61,8 +61,15 @@ class BarrierSubproblem:
         # rows with enforce_feasibility keep s = -c_ineq (N&W p. 576); done in
         # place on the caller's z, as the reference does (:92)
         s[self.enforce_feasibility] = -c_ineq[self.enforce_feasibility]
-        # scalar logs, then np.sum: the arithmetic of the reference (:93-95)
-        logs = [np.log(si) if si > 0 else -np.inf for si in s]
+        if s.shape[0] <= 4096:
+            # scalar logs, then np.sum: the arithmetic of the reference (:93-95),
+            # kept for small problems where runs are compared count for count
+            logs = [np.log(si) if si > 0 else -np.inf for si in s]
+        else:
+            # the per-element Python loop is O(n_ineq) interpreter work per function
+            # evaluation; vectorised, equal up to the last ulp of log
+            with np.errstate(divide='ignore', invalid='ignore'):
+                logs = np.where(s > 0, np.log(np.where(s > 0, s, 1.0)), -np.inf)
         return f - self.barrier_parameter * np.sum(logs)
 
     def _barrier_gradient(self, g):

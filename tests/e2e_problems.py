@@ -138,7 +138,65 @@ def _thomson(N, kind, method):
     return build
 
 
+# ---- small classics (Nocedal & Wright): equality, inequality + bounds, no
+# constraints at all (m = 0: Z = I), linear inequality, linear eq + ineq
+def _maratos(api):
+    """min 2(x^2 + y^2 - 1) - x  s.t.  x^2 + y^2 = 1 (ex. 15.4); x* = (1, 0)."""
+    th = np.pi / 3
+    x0 = np.array([np.cos(th), np.sin(th)])
+    con = api['NonlinearConstraint'](
+        lambda x: [x[0]**2 + x[1]**2], ("equals", 1),
+        lambda x: [[2 * x[0], 2 * x[1]]], lambda x, v: 2 * v[0] * np.eye(2))
+    return lambda: api['minimize_constrained'](
+        lambda x: 2 * (x[0]**2 + x[1]**2 - 1) - x[0], x0,
+        lambda x: np.array([4 * x[0] - 1, 4 * x[1]]), lambda x: 4 * np.eye(2), con)
+
+
+def _hyperbolic(api):
+    """min 1/2 (x-2)^2 + 1/2 (y-1/2)^2  s.t.  1/(x+1) - y >= 1/4, x, y >= 0
+    (ex. 19.1); x* = (1.952823, 0.088659)."""
+    def c_hess(x, v):
+        return 2 * v[0] * np.array([[1 / (x[0] + 1)**3, 0], [0, 0]])
+    con = [api['NonlinearConstraint'](lambda x: 1 / (x[0] + 1) - x[1], ("greater", 1 / 4),
+                                      lambda x: [[-1 / (x[0] + 1)**2, -1]], c_hess),
+           api['BoxConstraint'](("greater",))]
+    return lambda: api['minimize_constrained'](
+        lambda x: 1 / 2 * (x[0] - 2)**2 + 1 / 2 * (x[1] - 1 / 2)**2, np.array([0.0, 0.0]),
+        lambda x: np.array([x[0] - 2, x[1] - 1 / 2]), lambda x: np.eye(2), con)
+
+
+def _rosen_fun(x):
+    return 100 * (x[1] - x[0]**2)**2 + (1 - x[0])**2
+
+
+def _rosen_grad(x):
+    return np.array([-400 * x[0] * (x[1] - x[0]**2) - 2 * (1 - x[0]), 200 * (x[1] - x[0]**2)])
+
+
+def _rosen_hess(x):
+    return np.array([[1200 * x[0]**2 - 400 * x[1] + 2, -400 * x[0]], [-400 * x[0], 200.0]])
+
+
+def _rosenbrock(constraints):
+    def build(api):
+        x0 = np.array([-1.2, 1.0]) if constraints == "none" else np.array([-1.0, -0.5])
+        if constraints == "none":
+            con = ()
+        elif constraints == "ineq":
+            con = api['LinearConstraint'](np.array([[1.0, 2.0]]), ("less", 1))
+        else:
+            con = [api['LinearConstraint'](np.array([[1.0, 2.0]]), ("less", 1)),
+                   api['LinearConstraint'](np.array([[2.0, 1.0]]), ("equals", 1))]
+        return lambda: api['minimize_constrained'](_rosen_fun, x0, _rosen_grad, _rosen_hess, con)
+    return build
+
+
 PROBLEMS = {
+    "maratos": _maratos,
+    "hyperbolic_ineq": _hyperbolic,
+    "rosenbrock_unconstrained": _rosenbrock("none"),
+    "rosenbrock_ineq": _rosenbrock("ineq"),
+    "rosenbrock_eq_ineq": _rosenbrock("eqineq"),
     "eqp_window_2000": _eqp(2000, "window"),
     "eqp_rand_2000": _eqp(2000, "rand"),
     "eqp_window_20000": _eqp(20000, "window"),

@@ -136,9 +136,12 @@ def synth():
     print("synth_pcg.npz:", len(out), "arrays")
 
 
-def e2e():
-    out = {}
+def e2e(only=None):
+    path = os.path.join(HERE, "e2e.npz")
+    out = dict(np.load(path)) if (only and os.path.exists(path)) else {}
     for name, build in e2e_problems.PROBLEMS.items():
+        if only and name not in only:
+            continue
         prob = build(dict(minimize_constrained=minimize_constrained,
                           LinearConstraint=LinearConstraint,
                           BoxConstraint=BoxConstraint,
@@ -158,5 +161,8 @@ def e2e():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["kat", "synth", "e2e"]
-    for w in which:
-        {"kat": kat, "synth": synth, "e2e": e2e}[w]()
+    if which[0] == "e2e" and len(which) > 1:
+        e2e(only=which[1:])          # add / refresh the named problems only
+    else:
+        for w in which:
+            {"kat": kat, "synth": synth, "e2e": e2e}[w]()

@@ -80,3 +80,19 @@ def test_thomson_reaches_the_same_energy(api, gold, name):
     assert res.status in (1, 2)
     assert res.constr_violation < 1e-8
     assert res.fun == pytest.approx(fval, rel=1e-6)
+
+
+@pytest.mark.parametrize("name", ["maratos", "hyperbolic_ineq", "rosenbrock_unconstrained",
+                                  "rosenbrock_ineq", "rosenbrock_eq_ineq"])
+def test_small_classics(api, gold, name):
+    """Dense Jacobians (converted to CSR for the device), nonlinear equality
+    and inequality constraints with Hessians, bounds, and no constraints at
+    all (m = 0: Z is the identity).  These runs are short and well
+    conditioned: counts within +-1, solution to 1e-7."""
+    niter, cg, status, nfev, opt, viol, fval, radius = gold[name + "/scalars"]
+    res = e2e_problems.PROBLEMS[name](api)()
+    assert res.status == status
+    assert abs(res.niter - niter) <= 1 and abs(res.cg_niter - cg) <= 2
+    assert np.linalg.norm(res.x - gold[name + "/x"]) <= 1e-7 * max(1.0, np.linalg.norm(gold[name + "/x"]))
+    assert res.fun == pytest.approx(fval, rel=1e-8, abs=1e-12)
+    assert res.optimality < 1e-8 and res.constr_violation < 1e-8
