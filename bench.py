@@ -54,7 +54,8 @@ def algorithmic_bytes(n, m, nnzH, nnzA, nnzM, niter, inner_iters, n_z, n_refin, 
           B_in = B_spmv(m, m, nnzM) + 72 m     (one SpMV; fused update = 5 reads + 4 writes)
       inner CG iteration, A then A' (nnzM < 0):
           B_in = B_A + B_At + 8 m + 72 m       (two SpMVs, re-read of r for the dot)
-      one Z apply = 2 B_A + B_At + 8 n (+ its inner iterations), again per refinement
+      one Z apply = 2 B_A + B_At + 16 n (+ its inner iterations), again per refinement
+          (A x, A' v with the re-read of x, the orthogonality product A z, ||x||^2)
       outer iteration = B_H + 72 n (+ its Z apply)
 
     ``survey`` is the same launch priced with SURVEY.md section 8d's model
@@ -70,7 +71,7 @@ def algorithmic_bytes(n, m, nnzH, nnzA, nnzM, niter, inner_iters, n_z, n_refin, 
         B_M = None
         B_in = B_A + B_At + 8 * m + 72 * m
     B_in_survey = B_A + B_At + 56 * m
-    rest = (n_z + n_refin) * (2 * B_A + B_At + 8 * n) + n_hp * B_H + niter * 72 * n
+    rest = (n_z + n_refin) * (2 * B_A + B_At + 16 * n) + n_hp * B_H + niter * 72 * n
     total = inner_iters * B_in + rest
     survey = inner_iters * B_in_survey + rest
     return total, survey, dict(B_H=B_H, B_A=B_A, B_At=B_At, B_M=B_M, B_in=B_in,
@@ -542,7 +543,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--n", "--problem-size", dest="n", type=int, default=10_000_000)
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--pattern", default="window")
     ap.add_argument("--kappa", type=float, default=1e4)

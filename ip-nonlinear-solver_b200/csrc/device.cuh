@@ -879,9 +879,17 @@ __device__ __forceinline__ void normal_apply(const ProjView &P, const SyncView &
 //          beta = gamma'/gamma; alpha = gamma'/(delta' - beta*gamma'/alpha)
 // Every CTA returns the same iteration count.  fixed_iters > 0 runs exactly
 // that many iterations without a convergence test (bench only).
+// ``floor2``: squared norm of the vector being projected (>= 0 when known; with
+// floor_in_slot2 it is the global sum of slot 2, published by the caller).  The
+// residual target is rtol * max(||rhs||, ||x||): a vector that is already in
+// the null space to round-off (the second projection g = Z r of
+// qp_subproblem.py:504, refinement rounds) is not solved for its noise -- v = 0
+// is returned at once and the caller's orthogonality test (projections.py:72)
+// still decides whether a refinement solve is needed.
 __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
                                         Smem &sm, ProjStats &st,
-                                        int fixed_iters = 0) {
+                                        int fixed_iters = 0, bool floor_in_slot2 = false,
+                                        double floor2 = 0.0) {
     const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
     const int m = P.m;
     double a0;
@@ -897,16 +905,18 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
     normal_apply(P, S, sm, a0);
     publish(S, 0, a0, OP_SUM, sm.red);
     publish(S, 1, gpart, OP_SUM, sm.red);
-    set_ops(sm, OP_SUM, OP_SUM);
+    set_ops(sm, OP_SUM, OP_SUM, OP_SUM);
     grid_sync(S);
-    collect(S, sm, 2);
+    collect(S, sm, floor_in_slot2 ? 3 : 2);
     double delta = sm.out[0], gamma = sm.out[1];
+    if (floor_in_slot2) floor2 = sm.out[2];
     const double gamma0 = gamma;
     st.n_solves += 1;
     if (!(gamma0 > 0.0)) return 0;           // zero right-hand side: v = 0
+    const double target = P.rtol * P.rtol * fmax(gamma0, floor2);
+    if (fixed_iters <= 0 && gamma0 <= target) return 0;   // already orthogonal to round-off
     if (!(delta > 0.0)) { st.status = 5; return 0; }
     double alpha = gamma / delta, beta = 0.0;
-    const double target = P.rtol * P.rtol * gamma0;
     const int maxit = fixed_iters > 0 ? fixed_iters : P.maxit;
     int k = 0;
     while (k < maxit) {
@@ -955,10 +965,15 @@ __device__ __noinline__ double null_space(const ProjView &P, const SyncView &S,
         st.orth = 0.0;
         return sm.out[0];
     }
+    {
+        double xx = 0.0;                             // ||x||^2: floor of the solve's target
+        for (int i = gt; i < P.n; i += nt) { const double v = x[i]; xx += v * v; }
+        publish(S, 2, xx, OP_SUM, sm.red);
+    }
     a0 = a1 = 0.0;
     spmv(P.A, x, epi_plain(P.rhs), sm, S, a0, a1);
     grid_sync(S);
-    inner_solve(P, S, sm, st);
+    inner_solve(P, S, sm, st, 0, true);
     const double *src = x;
     double zz = 0.0;
     int k = 0;
@@ -992,7 +1007,8 @@ __device__ __noinline__ double null_space(const ProjView &P, const SyncView &S,
         if (ng != 0.0 && P.fro != 0.0) orth = sqrt(az) / (P.fro * ng);
         st.orth = orth;
         if (!(orth > P.orth_tol) || k >= P.max_refin) break;
-        // refine: solve M dv = A~ z, z -= A~' dv
+        // refine: solve M dv = A~ z, z -= A~' dv -- asked for by the caller's
+        // orth_tol, so to full relative accuracy (no floor)
         inner_solve(P, S, sm, st);
         st.n_refinements += 1;
         src = z;
