@@ -155,12 +155,10 @@ static SyncView sync_view(const ipb_ctx *ctx) {
     if (ctx->size > 1) {
         s.C.arena = (double *)ctx->arena;
         s.C.mbox = (double *)ctx->arena;
-        s.C.flag = (unsigned *)(ctx->arena + FLAG_OFF);
         s.C.seq = (unsigned *)(ctx->arena + SEQ_OFF);
         for (int q = 0; q < ctx->size; ++q) {
             s.C.peer_arena[q] = (double *)ctx->peer_base[q];
             s.C.peer_mbox[q] = (double *)ctx->peer_base[q];
-            s.C.peer_flag[q] = (unsigned *)(ctx->peer_base[q] + FLAG_OFF);
         }
         s.C.ghost_flag = (unsigned *)(ctx->arena + GFLAG_OFF);
         for (int k = 0; k < 2; ++k) {

@@ -83,8 +83,8 @@ constexpr int MAX_RANKS = 8;
 //   * all solver vectors of a rank live in one symmetric arena (same offsets
 //     on every rank), laid out [ghost_lo | own | ghost_hi]; a matrix's column
 //     indices are relative to the own part (negative / beyond the end = ghost);
-//   * before an SpMV the owners PUSH the entries their peers hold as ghosts
-//     (remote stores), then all ranks meet at a flag barrier;
+//   * before an SpMV the owners send the entries their peers hold as ghosts
+//     into the peers' ghost mailboxes (halo_sync); no barrier between ranks;
 //   * reductions: every rank posts its partial sums into every peer's mailbox
 //     and adds the mailbox up in rank order -- bit-identical on all ranks.
 struct SendList {
@@ -96,9 +96,7 @@ struct CommView {
     double *arena;            // this rank's arena
     double *peer_arena[MAX_RANKS];
     double *mbox;             // [4][MAX_RANKS][NSLOT] in this rank's memory
-    unsigned *flag;           // [size] last sequence number posted by each rank
     double *peer_mbox[MAX_RANKS];
-    unsigned *peer_flag[MAX_RANKS];
     unsigned *seq;            // sequence counter of this rank (persists across launches)
     SendList send[2];         // 0: n-space vectors, 1: m-space vectors
     // ghost mailboxes ("LL": 2 words {sequence, 32 bits} per entry, 4 generations)
@@ -314,15 +312,6 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *mbar) {
 }
 
 // ---------------------------------------------------------------- cross-GPU
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0,[%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0],%1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // Cross-GPU all-reduce of sm.out[0..nslots) in rank order, "LL" style: every
 // value travels as two 8-byte words {sequence number, 32 bits of the double},
 // so a word is its own arrival flag (8-byte stores are atomic over NVLink)

@@ -376,3 +376,23 @@ def test_full_size_properties(dev):
         if prev is not None:
             assert q < prev
         prev = q
+
+
+def test_results_do_not_alias_across_calls(dev):
+    """Large results come back in pinned buffers from a per-context pool: an
+    array the caller still holds must never be reused by a later call."""
+    n = 80_000
+    H, A, c, b = synthetic.make_qp(n, "window", 1e3, seed=0)
+    Z, LS, Y = dev.projections(A)
+    x1, _ = dev.qp.projected_cg(H, c, Z, Y, b, tol=1e-30, max_iter=2)
+    keep = x1.copy()
+    x2, _ = dev.qp.projected_cg(H, 2 * c, Z, Y, b, tol=1e-30, max_iter=2)
+    z1 = Z.dot(c)
+    z1_keep = z1.copy()
+    z2 = Z.dot(-c)
+    assert np.array_equal(x1, keep) and np.array_equal(z1, z1_keep)
+    assert not np.shares_memory(x1, x2) and not np.shares_memory(z1, z2)
+    assert_close(z2, -z1, 1e-12)
+    del x2, z2                    # buffers go back to the pool and are reused
+    x3, _ = dev.qp.projected_cg(H, c, Z, Y, b, tol=1e-30, max_iter=2)
+    assert np.array_equal(x3, keep) and np.array_equal(x1, keep)
