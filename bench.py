@@ -95,7 +95,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
