@@ -908,6 +908,7 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
     double alpha = gamma / delta, beta = 0.0;
     const int maxit = fixed_iters > 0 ? fixed_iters : P.maxit;
     int k = 0;
+    bool converged = false;
     while (k < maxit) {
         ++k;
         gpart = cg_update(P, sm, S, alpha, beta);
@@ -919,7 +920,7 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
         grid_sync(S);
         collect(S, sm, 2);
         double delta2 = sm.out[0], gamma2 = sm.out[1];
-        if (fixed_iters <= 0 && gamma2 <= target) break;
+        if (fixed_iters <= 0 && gamma2 <= target) { converged = true; break; }
         beta = gamma2 / gamma;
         double denom = delta2 - beta * gamma2 / alpha;
         if (!(denom > 0.0) || !(gamma2 == gamma2)) {
@@ -930,9 +931,11 @@ __device__ __noinline__ int inner_solve(const ProjView &P, const SyncView &S,
         gamma = gamma2;
     }
     st.inner_iters += k;
-    if (fixed_iters <= 0 && k >= maxit && st.status == 0) {
-        // not converged to rtol: leave it to the refinement loop / caller
-    }
+    // maxit reached without meeting the target (the loop leaves by `break` when
+    // it converges): rank-deficient A with a right-hand side outside its range,
+    // or a system too ill-conditioned for inner_maxit -- fail loudly, as the
+    // reference does when its factorisation is singular (projections.py:101-108)
+    if (fixed_iters <= 0 && !converged && st.status == 0) st.status = 5;
     return k;
 }
 

@@ -396,3 +396,21 @@ def test_results_do_not_alias_across_calls(dev):
     del x2, z2                    # buffers go back to the pool and are reused
     x3, _ = dev.qp.projected_cg(H, c, Z, Y, b, tol=1e-30, max_iter=2)
     assert np.array_equal(x3, keep) and np.array_equal(x1, keep)
+
+
+def test_rank_deficient_jacobian_fails_loudly(dev):
+    """A with a repeated row: A A' is singular.  Z x only needs a consistent
+    system and still works; Y b with b outside the range of A has no solution
+    -- the reference's factorisation raises and falls back to a dense SVD
+    (projections.py:101-108), the device path raises InnerSolveError instead of
+    returning garbage."""
+    rng = np.random.RandomState(0)
+    A = sps.random(40, 200, density=0.05, random_state=rng, format='csr')
+    A = sps.vstack([A, A[3]]).tocsr()                 # row 40 == row 3
+    Z, LS, Y = dev.projections(A)
+    x = rng.standard_normal(200)
+    z = Z.dot(x)
+    assert np.linalg.norm(A.dot(z)) <= 1e-10 * np.linalg.norm(x)
+    b = rng.standard_normal(41)                       # b[40] != b[3]: inconsistent
+    with pytest.raises(dev.device.InnerSolveError):
+        Y.dot(b)
