@@ -424,14 +424,25 @@ def run_b200_dist(args):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gloo = dist.new_group(backend="gloo")
     n, m = args.n, args.n // 2
+    hashed = args.pattern == "hashed"
     t0 = time.perf_counter()
-    H, A, c, b = synthetic.make_qp(n, args.pattern, args.kappa, seed=0)
-    t_gen = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    S = D.DistSolver(H, A, rank, size, group=gloo, device=local, inner_rtol=args.inner_rtol)
+    if hashed:
+        # index-addressable problem: each rank generates a window around its own rows
+        H = A = c = b = None
+        t_gen = 0.0
+        S = D.DistSolver(None, None, rank, size, group=gloo, device=local,
+                         inner_rtol=args.inner_rtol,
+                         generated=dict(n=n, kappa=args.kappa, seed=0))
+        (n0, n1), (m0, m1) = S.part.own(rank, 0), S.part.own(rank, 1)
+        c_loc, b_loc = synthetic.hashed_vectors(n0, n1, m0, m1, 0)
+    else:
+        H, A, c, b = synthetic.make_qp(n, args.pattern, args.kappa, seed=0)
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        S = D.DistSolver(H, A, rank, size, group=gloo, device=local, inner_rtol=args.inner_rtol)
+        c_loc, b_loc = S.local(c, 0), S.local(b, 1)
     t_setup = time.perf_counter() - t0
     ctx = S.ctx
-    c_loc, b_loc = S.local(c, 0), S.local(b, 1)
     dc, db = S.vector(c_loc), S.vector(b_loc, space=1)
     dx = S.vector(space=0)
 
@@ -483,21 +494,24 @@ def run_b200_dist(args):
 
     # roofline of the solve kernel: whole-problem bytes over the max-over-ranks time
     i0 = infos[-1]
-    nnzM = 0
-    nnzM_loc = torch.tensor([S.parts["M"].nnz], dtype=torch.int64, device="cuda")
-    dist.all_reduce(nnzM_loc)
-    nnzM = int(nnzM_loc.item())
+    nnz_loc = torch.tensor([S.parts["M"].nnz, S.parts["H"].nnz, S.parts["A_raw"].nnz],
+                           dtype=torch.int64, device="cuda")
+    dist.all_reduce(nnz_loc)
+    nnzM, nnzH, nnzA = (int(v) for v in nnz_loc.tolist())
     n_z = int(i0.n_solves) - int(i0.n_refinements) - 1
     bytes_launch, bytes_survey, parts = algorithmic_bytes(
-        n, m, H.nnz, A.nnz, nnzM, int(i0.niter), int(i0.inner_iters), n_z,
+        n, m, nnzH, nnzA, nnzM, int(i0.niter), int(i0.inner_iters), n_z,
         int(i0.n_refinements), int(i0.n_spmv_h))
     t = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     avg_ms = float(t.item())
     peak, peak_src = peaks()
     achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
-    x_all = S.gather(dx.download())
-    feas = float(np.linalg.norm(A.dot(x_all) + b) / np.linalg.norm(b))
+    if hashed:
+        feas = None            # nobody holds the whole A; parity is scripts/dist_check.py's job
+    else:
+        x_all = S.gather(dx.download())
+        feas = float(np.linalg.norm(A.dot(x_all) + b) / np.linalg.norm(b))
     if rank == 0:
         cfg = workload_config(args)
         line = {

@@ -77,35 +77,12 @@ def _localize(M, lo, hi, ghosts_lo, ghosts_hi):
     return L
 
 
-def local_parts(part, rank, H, A):
-    """This rank's pieces of the QP matrices, in local column numbering.
-
-    ``H`` (n x n) and ``A`` (m x n) are the global scipy matrices (every rank
-    holds them -- fine up to n ~ 1e7; generating per partition is the next
-    step for config 5).  Returns a dict with CSR matrices ``H``, ``A_raw``,
-    ``A_norm``, ``At_raw``, ``At_norm``, ``M`` whose column indices are
-    relative to the rank's own block, the per-space ghost index lists
-    (global indices, ascending, split below / above the own block), the
-    row scaling of the own rows and ``||A||_F``."""
-    H = sps.csr_matrix(H)
-    A = sps.csr_matrix(A)
+def _assemble(part, rank, H_rows, A_rows, An_rows, At_rows, Ant_rows, M_rows, dscale_own,
+              fro2_own):
+    """Local column numbering + ghost lists from this rank's row blocks (all
+    with GLOBAL column indices)."""
     n0, n1 = part.own(rank, N_SPACE)
     m0, m1 = part.own(rank, M_SPACE)
-    row_norm2 = np.asarray(A.multiply(A).sum(axis=1)).ravel()
-    dscale = np.where(row_norm2 > 0, 1.0 / np.sqrt(np.where(row_norm2 > 0, row_norm2, 1.0)), 0.0)
-    fro = float(np.sqrt(row_norm2.sum()))
-    An = sps.diags(dscale) @ A                       # row-normalised A
-    An = sps.csr_matrix(An)
-    An.sort_indices()
-    A_rows, An_rows = A[m0:m1], An[m0:m1]
-    At = sps.csr_matrix(A.T)
-    At.sort_indices()
-    Ant = sps.csr_matrix(An.T)
-    Ant.sort_indices()
-    At_rows, Ant_rows = At[n0:n1], Ant[n0:n1]
-    M_rows = sps.csr_matrix(An_rows @ An.T)          # own rows of A~ A~'
-    M_rows.sort_indices()
-    H_rows = H[n0:n1]
     # ghost entries per space: union over the matrices whose columns live there
     gn = np.union1d(_remote_columns(H_rows, n0, n1), _remote_columns(A_rows, n0, n1))
     gm = np.union1d(_remote_columns(At_rows, m0, m1), _remote_columns(M_rows, m0, m1))
@@ -115,9 +92,94 @@ def local_parts(part, rank, H, A):
     return {
         "H": loc_n(H_rows), "A_raw": loc_n(A_rows), "A_norm": loc_n(An_rows),
         "At_raw": loc_m(At_rows), "At_norm": loc_m(Ant_rows), "M": loc_m(M_rows),
-        "ghosts": ghosts, "dscale": dscale[m0:m1].copy(), "fro": fro,
+        "ghosts": ghosts, "dscale": np.ascontiguousarray(dscale_own), "fro2_own": float(fro2_own),
         "own": {N_SPACE: (n0, n1), M_SPACE: (m0, m1)},
     }
+
+
+def _row_scaling(A):
+    row_norm2 = np.asarray(A.multiply(A).sum(axis=1)).ravel()
+    dscale = np.where(row_norm2 > 0, 1.0 / np.sqrt(np.where(row_norm2 > 0, row_norm2, 1.0)), 0.0)
+    return row_norm2, dscale
+
+
+def local_parts(part, rank, H, A):
+    """This rank's pieces of the QP matrices, in local column numbering.
+
+    ``H`` (n x n) and ``A`` (m x n) are the global scipy matrices (every rank
+    holds them -- fine up to n ~ 1e7; :func:`local_parts_generated` builds the
+    same pieces from the rank's own rows only).  Returns a dict with CSR
+    matrices ``H``, ``A_raw``, ``A_norm``, ``At_raw``, ``At_norm``, ``M`` whose
+    column indices are relative to the rank's own block, the per-space ghost
+    index lists (global indices, ascending, split below / above the own
+    block), the row scaling of the own rows and ``||A||_F``."""
+    H = sps.csr_matrix(H)
+    A = sps.csr_matrix(A)
+    n0, n1 = part.own(rank, N_SPACE)
+    m0, m1 = part.own(rank, M_SPACE)
+    row_norm2, dscale = _row_scaling(A)
+    An = sps.csr_matrix(sps.diags(dscale) @ A)       # row-normalised A
+    An.sort_indices()
+    At = sps.csr_matrix(A.T)
+    At.sort_indices()
+    Ant = sps.csr_matrix(An.T)
+    Ant.sort_indices()
+    M_rows = sps.csr_matrix(An[m0:m1] @ An.T)        # own rows of A~ A~'
+    M_rows.sort_indices()
+    out = _assemble(part, rank, H[n0:n1], A[m0:m1], An[m0:m1], At[n0:n1], Ant[n0:n1], M_rows,
+                    dscale[m0:m1], row_norm2[m0:m1].sum())
+    out["fro"] = float(np.sqrt(row_norm2.sum()))
+    return out
+
+
+def local_parts_generated(part, rank, kappa=1e4, seed=0, margin=16):
+    """The same pieces for the index-addressable synthetic QP
+    (``synthetic.hashed_*``), built from a WINDOW of rows around the rank's own
+    block: no rank ever holds the whole problem (BASELINE config 5).  The
+    window holds every row of A that touches the rank's variables or shares a
+    column with one of its rows (the Jacobian's columns stay within +-8 of the
+    pivot 2i, so ``margin`` rows on each side are enough); ``fro`` is missing
+    -- the caller sums ``fro2_own`` over the ranks."""
+    from . import synthetic
+    n, m = part.n, part.m
+    n0, n1 = part.own(rank, N_SPACE)
+    m0, m1 = part.own(rank, M_SPACE)
+    w0 = max(0, min(m0, n0 // 2) - margin)
+    w1 = min(m, max(m1, n1 // 2 + 1) + margin)
+    A_win = synthetic.hashed_jacobian_rows(n, w0, w1, seed)          # global columns
+    c_lo = int(A_win.indices.min()) if A_win.nnz else 0
+    c_hi = int(A_win.indices.max()) + 1 if A_win.nnz else 1
+    assert c_lo <= n0 or n0 == n1 or w0 == 0, "window does not cover the own variables"
+    # the window in its own coordinates: (w1 - w0) x (c_hi - c_lo)
+    Aw = sps.csr_matrix((A_win.data, A_win.indices - c_lo, A_win.indptr),
+                        shape=(w1 - w0, c_hi - c_lo))
+    row_norm2, dscale = _row_scaling(Aw)
+    Anw = sps.csr_matrix(sps.diags(dscale) @ Aw)
+    Anw.sort_indices()
+    Atw = sps.csr_matrix(Aw.T)
+    Atw.sort_indices()
+    Antw = sps.csr_matrix(Anw.T)
+    Antw.sort_indices()
+    r0, r1 = m0 - w0, m1 - w0                                         # own rows in the window
+    Mw = sps.csr_matrix(Anw[r0:r1] @ Anw.T)
+    Mw.sort_indices()
+
+    def to_global(X, col_off, ncols):
+        X = sps.csr_matrix(X)
+        return sps.csr_matrix((X.data, X.indices.astype(np.int64) + col_off, X.indptr),
+                              shape=(X.shape[0], ncols))
+    v0, v1 = max(n0 - c_lo, 0), max(min(n1 - c_lo, c_hi - c_lo), 0)   # own variables in the window
+    At_rows, Ant_rows = Atw[v0:v1], Antw[v0:v1]
+    if (n1 - n0) != (v1 - v0):          # own variables no row of the window touches: empty rows
+        pad_lo, pad_hi = max(c_lo - n0, 0), max(n1 - c_hi, 0)
+        z = lambda k: sps.csr_matrix((k, w1 - w0))                    # noqa: E731
+        At_rows = sps.vstack([z(pad_lo), At_rows, z(pad_hi)], "csr")
+        Ant_rows = sps.vstack([z(pad_lo), Ant_rows, z(pad_hi)], "csr")
+    H_rows = synthetic.hashed_hessian_rows(n, n0, n1, kappa, seed)
+    return _assemble(part, rank, H_rows, to_global(Aw[r0:r1], c_lo, n),
+                     to_global(Anw[r0:r1], c_lo, n), to_global(At_rows, w0, m),
+                     to_global(Ant_rows, w0, m), to_global(Mw, w0, m), dscale[r0:r1],
+                     row_norm2[r0:r1].sum())
 
 
 def send_lists(part, rank, all_ghosts, glo_cap=None):
@@ -190,13 +252,27 @@ class DistSolver:
     """
 
     def __init__(self, H, A, rank, size, group=None, device=None, inner_rtol=1e-13,
-                 inner_maxit=1000, orth_tol=1e-12, max_refin=3, explicit_aat=True):
+                 inner_maxit=1000, orth_tol=1e-12, max_refin=3, explicit_aat=True,
+                 generated=None):
+        """``H``, ``A``: the global matrices (every rank holds them), or None with
+        ``generated=dict(n=..., kappa=..., seed=...)``: the index-addressable
+        synthetic QP, each rank generating only a window around its own rows."""
         import torch.distributed as dist
         from . import device as dev
         self.rank, self.size = int(rank), int(size)
-        n, m = H.shape[0], A.shape[0]
-        self.part = RowPartition(n, m, size)
-        parts = local_parts(self.part, rank, H, A)
+        if generated is not None:
+            n = int(generated["n"])
+            m = n // 2
+            self.part = RowPartition(n, m, size)
+            parts = local_parts_generated(self.part, rank, generated.get("kappa", 1e4),
+                                          generated.get("seed", 0))
+            fro2 = [None] * size
+            dist.all_gather_object(fro2, parts["fro2_own"], group=group)
+            parts["fro"] = float(np.sqrt(sum(fro2)))
+        else:
+            n, m = H.shape[0], A.shape[0]
+            self.part = RowPartition(n, m, size)
+            parts = local_parts(self.part, rank, H, A)
         self.parts = parts
         all_ghosts = [None] * size
         dist.all_gather_object(all_ghosts, parts["ghosts"], group=group)

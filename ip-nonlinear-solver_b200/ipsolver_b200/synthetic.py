@@ -71,3 +71,73 @@ def make_qp(n, pattern='window', kappa=1e4, seed=0):
     A = sparse_jacobian(n, m, pattern, seed + 1)
     c, b = qp_vectors(n, m, seed + 2)
     return H, A, c, b
+
+
+# ---------------------------------------------------------------------------
+# index-addressable variant ("hashed"): every entry is a pure function of
+# (seed, stream, index), so any block of rows can be generated on its own --
+# what a row-partitioned run at n = 1e8 (BASELINE config 5) needs: no rank
+# ever holds the whole problem.  Same structure as above (5-diagonal SPD H
+# with log-uniform diagonal in [1, kappa]; A with pivot 2.5+U(0,1) at column
+# 2i and two U(-1,1) entries within +-8 columns), different random stream.
+# ---------------------------------------------------------------------------
+_MASK = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _u01(seed, stream, idx):
+    """Uniform(0,1) doubles, a splitmix64 hash of (seed, stream, idx)."""
+    with np.errstate(over='ignore'):
+        z = (np.asarray(idx, dtype=np.uint64)
+             + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+             + np.uint64(stream) * np.uint64(0xD1B54A32D192ED03))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def _normal(seed, stream, idx):
+    u1, u2 = _u01(seed, stream, idx), _u01(seed, stream + 1, idx)
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def hashed_hessian_rows(n, r0, r1, kappa=1e4, seed=0):
+    """Rows [r0, r1) of the n x n Hessian, CSR with GLOBAL column indices."""
+    i = np.arange(r0, r1, dtype=np.int64)
+    diag = kappa ** _u01(seed, 0, i)
+    off = lambda stream, k: 0.2 * (2.0 * _u01(seed, stream, k) - 1.0)   # noqa: E731
+    cols = np.stack([i - 2, i - 1, i, i + 1, i + 2], axis=1)
+    # entry (i, i+1) is off1[i], (i, i-1) is off1[i-1]; same for the second diagonal
+    vals = np.stack([off(2, i - 2), off(1, i - 1), diag, off(1, i), off(2, i)], axis=1)
+    keep = (cols >= 0) & (cols < n)
+    indptr = np.concatenate(([0], np.cumsum(keep.sum(axis=1))))
+    return sps.csr_matrix((vals[keep], cols[keep], indptr), shape=(r1 - r0, n))
+
+
+def hashed_jacobian_rows(n, r0, r1, seed=0):
+    """Rows [r0, r1) of the (n/2) x n windowed Jacobian, CSR with GLOBAL columns."""
+    i = np.arange(r0, r1, dtype=np.int64)
+    pivot = 2 * i
+    e1 = np.clip(pivot + np.floor(16.0 * _u01(seed, 10, 2 * i)).astype(np.int64) - 8, 0, n - 1)
+    e2 = np.clip(pivot + np.floor(16.0 * _u01(seed, 10, 2 * i + 1)).astype(np.int64) - 8, 0, n - 1)
+    cols = np.stack([pivot, e1, e2], axis=1).ravel()
+    vals = np.stack([2.5 + _u01(seed, 11, i), 2.0 * _u01(seed, 12, 2 * i) - 1.0,
+                     2.0 * _u01(seed, 12, 2 * i + 1) - 1.0], axis=1).ravel()
+    rows = np.repeat(np.arange(r1 - r0, dtype=np.int64), 3)
+    A = sps.coo_matrix((vals, (rows, cols)), shape=(r1 - r0, n)).tocsr()
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
+
+
+def hashed_vectors(n0, n1, m0, m1, seed=0):
+    """c[n0:n1] and b[m0:m1] of the hashed problem."""
+    return (_normal(seed, 20, np.arange(n0, n1, dtype=np.int64)),
+            _normal(seed, 22, np.arange(m0, m1, dtype=np.int64)))
+
+
+def make_qp_hashed(n, kappa=1e4, seed=0):
+    """The whole hashed problem (for tests and single-GPU comparison)."""
+    m = n // 2
+    c, b = hashed_vectors(0, n, 0, m, seed)
+    return hashed_hessian_rows(n, 0, n, kappa, seed), hashed_jacobian_rows(n, 0, m, seed), c, b

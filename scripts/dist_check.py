@@ -20,10 +20,18 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 gloo = dist.new_group(backend="gloo")
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 200_000
 pattern = sys.argv[2] if len(sys.argv) > 2 else 'window'
-H, A, c, b = synthetic.make_qp(n, pattern, 1e4, 0)
+if pattern == 'hashed':
+    # every rank generates only a window around its own rows; rank 0 alone also
+    # builds the whole problem, for the single-GPU comparison
+    H, A, c, b = synthetic.make_qp_hashed(n, 1e4, 0)
+    t0 = time.perf_counter()
+    S = D.DistSolver(None, None, rank, size, group=gloo, device=local,
+                     generated=dict(n=n, kappa=1e4, seed=0))
+else:
+    H, A, c, b = synthetic.make_qp(n, pattern, 1e4, 0)
+    t0 = time.perf_counter()
+    S = D.DistSolver(H, A, rank, size, group=gloo, device=local)
 lbg, ubg = synthetic.box_bounds(n, 1.5)
-t0 = time.perf_counter()
-S = D.DistSolver(H, A, rank, size, group=gloo, device=local)
 if rank == 0:
     print("setup %.2f s; ghosts n-space %s m-space %s" % (
         time.perf_counter() - t0, [len(g) for g in S.parts["ghosts"][0]],

@@ -131,3 +131,31 @@ def test_gloo_world_size_2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % r in o
+
+
+@pytest.mark.parametrize("n", [4000, 50, 14])
+@pytest.mark.parametrize("size", [1, 2, 3, 8])
+def test_generated_parts_equal_sliced_parts(n, size):
+    """BASELINE config 5 path: each rank builds its pieces from a window of the
+    index-addressable synthetic QP; they must be the pieces sliced out of the
+    whole problem."""
+    H, A, c, b = synthetic.make_qp_hashed(n, 1e4, 0)
+    assert abs(H - H.T).max() == 0 and A.shape == (n // 2, n)
+    part = D.RowPartition(n, n // 2, size)
+    fro2 = 0.0
+    for g in range(size):
+        a, w = D.local_parts(part, g, H, A), D.local_parts_generated(part, g, 1e4, 0)
+        for k in ("H", "A_raw", "A_norm", "At_raw", "At_norm", "M"):
+            assert np.array_equal(a[k].indptr, w[k].indptr), k
+            assert np.array_equal(a[k].indices, w[k].indices), k
+            np.testing.assert_allclose(a[k].data, w[k].data, rtol=1e-15, atol=0)
+        for sp in (0, 1):
+            for j in (0, 1):
+                assert np.array_equal(a["ghosts"][sp][j], w["ghosts"][sp][j])
+        assert np.array_equal(a["dscale"], w["dscale"])
+        n0, n1 = part.own(g, 0)
+        m0, m1 = part.own(g, 1)
+        cl, bl = synthetic.hashed_vectors(n0, n1, m0, m1, 0)
+        assert np.array_equal(cl, c[n0:n1]) and np.array_equal(bl, b[m0:m1])
+        fro2 += w["fro2_own"]
+    assert np.sqrt(fro2) == pytest.approx(a["fro"], rel=1e-13)
