@@ -13,7 +13,7 @@ import numpy as np
 import scipy.sparse as sps
 from scipy.sparse.linalg import LinearOperator
 
-from .device import Context, DeviceCSR, DeviceHessian, _bounds
+from .device import Context, DeviceCSR, DeviceHessian
 from ._cabi import dptr, f64
 from .projections import DeviceMap
 
