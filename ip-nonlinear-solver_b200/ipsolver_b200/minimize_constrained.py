@@ -16,6 +16,7 @@ Hessians (``hess='2-point'`` ...) are host callbacks and are not supported:
 Lagrangian Hessian can be applied on the device.
 """
 import time
+import warnings
 
 import numpy as np
 import scipy.sparse as sps
@@ -80,6 +81,26 @@ def _bounds_of(kind, m):
     if (vals[0] > vals[1]).any():
         raise ValueError("lb[i] > ub[i].")
     return vals[0], vals[1]
+
+
+def _inside_box(box, x0, rel=0.01, absol=0.01):
+    """Entries of x0 whose bounds are to be kept feasible throughout are moved a
+    little inside them (by ``absol``, or ``rel`` of the interval if that is
+    less) -- reference ``_reinforce_box_constraint`` (_constraints.py:449-477)."""
+    m = x0.shape[0]
+    enforce = np.broadcast_to(np.asarray(box.enforce_feasibility, dtype=bool), (m,))
+    lb, ub = _bounds_of(box.kind, m)
+    if not (enforce & ((x0 < lb) | (x0 > ub))).any():
+        return x0
+    with np.errstate(invalid='ignore'):
+        low = np.minimum(lb + absol, lb + rel * (ub - lb))
+        up = np.maximum(ub - absol, ub - rel * (ub - lb))
+    x = x0.copy()
+    sel = enforce & np.isfinite(lb)
+    x[sel] = np.maximum(x[sel], low[sel])
+    sel = enforce & np.isfinite(ub)
+    x[sel] = np.minimum(x[sel], up[sel])
+    return x
 
 
 class _Rows:
@@ -216,10 +237,20 @@ def minimize_constrained(fun, x0, grad, hess, constraints=(), method=None, xtol=
         raise TypeError("ipsolver_b200.minimize_constrained needs `hess` as a callable returning "
                         "a scipy sparse matrix or an ndarray; finite-difference Hessians are host "
                         "callbacks outside the device path.")
+    # as in the reference, f0 and g0 are taken at the x0 the caller passed, BEFORE
+    # a box with enforce_feasibility moves it (_minimize_constrained.py:378-379 vs
+    # :431-432) -- a quirk that shapes the first iteration and is kept for parity
     f0 = fun(x0)
     g0 = np.atleast_1d(grad(x0))
     if isinstance(constraints, (NonlinearConstraint, LinearConstraint, BoxConstraint)):
         constraints = [constraints]
+    for con in constraints:                      # reference _constraints.py:315-344
+        if isinstance(con, BoxConstraint):
+            x_in = _inside_box(con, x0)
+            if not np.array_equal(x_in, x0):
+                warnings.warn("The initial point was changed in order to stay inside box "
+                              "constraints.")
+                x0 = x_in
     canon = _Canonical([_rows_of(c, x0, sparse_jacobian) for c in constraints], n_vars,
                        sparse_jacobian)
     c_ineq0, c_eq0 = canon.constr(x0)

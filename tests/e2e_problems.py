@@ -191,7 +191,17 @@ def _rosenbrock(constraints):
     return build
 
 
+def _rosenbrock_box_enforced(api):
+    """Rosenbrock in a box that must stay feasible at every iterate
+    (``enforce_feasibility``): the infeasible start is moved inside and the
+    slack of those rows follows the constraint (N&W p. 576)."""
+    con = api['BoxConstraint'](("interval", [-0.5, -0.5], [0.4, 0.3]), enforce_feasibility=True)
+    return lambda: api['minimize_constrained'](_rosen_fun, np.array([-1.2, 1.0]), _rosen_grad,
+                                               _rosen_hess, con)
+
+
 PROBLEMS = {
+    "rosenbrock_box_enforced": _rosenbrock_box_enforced,
     "maratos": _maratos,
     "hyperbolic_ineq": _hyperbolic,
     "rosenbrock_unconstrained": _rosenbrock("none"),

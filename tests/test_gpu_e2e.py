@@ -83,7 +83,8 @@ def test_thomson_reaches_the_same_energy(api, gold, name):
 
 
 @pytest.mark.parametrize("name", ["maratos", "hyperbolic_ineq", "rosenbrock_unconstrained",
-                                  "rosenbrock_ineq", "rosenbrock_eq_ineq"])
+                                  "rosenbrock_ineq", "rosenbrock_eq_ineq",
+                                  "rosenbrock_box_enforced"])
 def test_small_classics(api, gold, name):
     """Dense Jacobians (converted to CSR for the device), nonlinear equality
     and inequality constraints with Hessians, bounds, and no constraints at

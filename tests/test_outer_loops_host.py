@@ -28,7 +28,8 @@ def run(name):
 @pytest.mark.parametrize("name", ["eqp_window_2000", "eqp_rand_2000", "eqp_window_2000_gtol6",
                                   "ipqp_window_1000", "thomson_20_equals", "thomson_20_less",
                                   "maratos", "hyperbolic_ineq", "rosenbrock_unconstrained",
-                                  "rosenbrock_ineq", "rosenbrock_eq_ineq"])
+                                  "rosenbrock_ineq", "rosenbrock_eq_ineq",
+                                  "rosenbrock_box_enforced"])
 def test_outer_loop_reproduces_reference(golden_dir, name):
     import os
     gold = np.load(os.path.join(golden_dir, "e2e.npz"))
