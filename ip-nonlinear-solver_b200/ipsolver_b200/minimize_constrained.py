@@ -21,6 +21,7 @@ import warnings
 import numpy as np
 import scipy.sparse as sps
 from scipy.optimize import OptimizeResult
+from scipy.sparse.linalg import LinearOperator
 
 from .equality_constrained_sqp import equality_constrained_sqp, device_hot_path
 from .tr_interior_point import tr_interior_point
@@ -258,6 +259,10 @@ def minimize_constrained(fun, x0, grad, hess, constraints=(), method=None, xtol=
 
     def lagr_hess(x, v_eq=np.empty(0), v_ineq=np.empty(0)):
         H0 = hess(x)
+        if isinstance(H0, LinearOperator):
+            raise TypeError("`hess` returned a LinearOperator: the device path needs the Hessian "
+                            "as a scipy sparse matrix or an ndarray (opaque operators are host "
+                            "callbacks; keep the reference's scipy path for them).")
         H0 = sps.csr_matrix(H0) if sps.issparse(H0) else np.atleast_2d(np.asarray(H0))
         return hp.hessian(len(x), [H0] + canon.hess_terms(x, v_eq, v_ineq))
 

@@ -63,3 +63,20 @@ def test_fd_hessian_is_rejected():
     with pytest.raises(TypeError):
         ipb.minimize_constrained(lambda x: x.dot(x), np.ones(3), lambda x: 2 * x, '2-point',
                                  hot_path=ORACLE_PATH)
+
+
+def test_operator_hessian_is_rejected():
+    from scipy.sparse.linalg import aslinearoperator
+    with pytest.raises(TypeError):
+        ipb.minimize_constrained(lambda x: x.dot(x), np.ones(3), lambda x: 2 * x,
+                                 lambda x: aslinearoperator(2 * np.eye(3)), hot_path=ORACLE_PATH)
+
+
+def test_callback_and_return_all():
+    seen = []
+    res = ipb.minimize_constrained(
+        e2e_problems._rosen_fun, np.array([-1.2, 1.0]), e2e_problems._rosen_grad,
+        e2e_problems._rosen_hess, (), hot_path=ORACLE_PATH, options={"return_all": True},
+        callback=lambda state: seen.append(state.niter) or len(seen) >= 5)
+    assert res.status == 3 and len(seen) == 5          # the callback asked to stop
+    assert len(res.allvecs) == res.niter and len(res.allmult) == res.niter
