@@ -51,7 +51,9 @@ typedef struct {
     int32_t hits_boundary;    /* info['hits_boundary']                           */
     int32_t status;           /* ipb_status raised inside the kernel             */
     int32_t n_allvecs;        /* vectors stored when return_all was requested    */
-    int64_t inner_iters;      /* CG iterations on A A' summed over all solves    */
+    int64_t inner_iters;      /* inner iterations on A A' summed over all solves:
+                               * CG iterations, or residual-checked sweeps of the
+                               * banded direct solve                            */
     int64_t n_solves;         /* number of (A A')^-1 solves                      */
     int64_t n_refinements;    /* iterative-refinement rounds (projections.py:72) */
     int64_t n_spmv_h;         /* H products                                      */
@@ -66,7 +68,7 @@ typedef struct {
     int64_t n_solves;
     int64_t n_refinements;
     int32_t status;
-    int32_t reserved;
+    int32_t n_fallbacks;      /* banded direct solves given up for CG (0 normally) */
     double  orth;             /* orthogonality(A, z) of the returned z (Z only)  */
     double  kernel_ms;
 } ipb_proj_info;
@@ -124,8 +126,9 @@ int ipb_hess_matvec_dev(ipb_ctx *ctx, const ipb_hess *h, const ipb_vec *x, ipb_v
 /* Replaces projections(A, method, orth_tol, max_refin, tol) for sparse A
  * (projections.py:290-406; NormalEquation :58-90, AugmentedSystem :93-172).
  * (A A')^-1 is applied by a conjugate-gradient iteration on the row-normalised
- * A (Jacobi-preconditioned CG on A A'), never by a factorisation.  A is
- * borrowed and must have been created with_transpose. */
+ * A (Jacobi-preconditioned CG on A A'), or -- when A A' is banded -- by the
+ * banded direct solve below with the CG as its fallback.  A is borrowed and
+ * must have been created with_transpose. */
 int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int max_refin,
                     double inner_rtol, int inner_maxit, ipb_proj **out);
 /* How (A A') is applied inside the inner CG: mode 0 (default) keeps the explicit
@@ -135,7 +138,21 @@ int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int max_refin,
  * values on every refresh.  ipb_proj_aat_nnz: nnz(M), or -1 when not held. */
 int ipb_proj_set_aat_mode(ipb_ctx *ctx, ipb_proj *p, int mode);
 int64_t ipb_proj_aat_nnz(const ipb_proj *p);
-/* call after ipb_csr_update_values(A): refreshes row norms, ||A||_F, A', M. */
+/* Banded direct solve.  When M = A~ A~' is banded (half-bandwidth 1..7 -- a
+ * Jacobian whose rows touch a narrow window of columns), its Cholesky factor
+ * is kept in HBM and (A A')^-1 is applied by overlapping-chunk substitution
+ * sweeps: exact to round-off for these matrices (the reference applies a
+ * factorisation too: CHOLMOD projections.py:62, SuperLU :102), every solve is
+ * verified by its residual and refined, and a solve whose residual does not
+ * contract falls back to the CG (and switches the factor off).
+ *   mode 0: use it when M is banded (default), 1: never;
+ *   chunk_rows / overlap: 0 = defaults (chunk sized to the GPU, overlap 48).
+ * ipb_proj_band_info: out[6] = {in use, half-bandwidth of M (-1 unknown),
+ *   chunk rows, overlap, groups of 32 chunks, factor still trusted}. */
+int ipb_proj_set_band(ipb_ctx *ctx, ipb_proj *p, int mode, int chunk_rows, int overlap);
+int ipb_proj_band_info(ipb_ctx *ctx, const ipb_proj *p, int32_t *out);
+/* call after ipb_csr_update_values(A): refreshes row norms, ||A||_F, A', M and
+ * the banded factor. */
 int ipb_proj_refresh(ipb_ctx *ctx, ipb_proj *p);
 int ipb_proj_destroy(ipb_ctx *ctx, ipb_proj *p);
 /* Z: z = x - A'(AA')^-1 A x with refinement (null_space closures :65-80, :114-142) */
@@ -263,7 +280,8 @@ int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x,
  * a grid barrier after each (0: fused vector update, 1: A' r, 2: A t, 3: M r,
  * 4: barrier only, 5: the bulk-copy pipeline of M r without the arithmetic,
  * 6: barrier + cross-GPU all-reduce, 7: barrier + ghost push of an m-vector,
- * 8: the row arithmetic of M r without the copy pipeline);
+ * 8: the row arithmetic of M r without the copy pipeline, 9: one sweep of the
+ * banded direct solve);
  * returns device milliseconds.  Results are discarded and
  * the projector's work vectors are overwritten. */
 int ipb_bench_phase(ipb_ctx *ctx, ipb_proj *p, int phase, int reps, double *ms);

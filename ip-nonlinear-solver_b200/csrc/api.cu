@@ -67,6 +67,13 @@ struct ipb_proj {
     double *m_val = nullptr;
     int4 *m_desc = nullptr;
     int m_nblk = 0;
+    // banded Cholesky factor of M, applied in overlapping chunks (BandView)
+    int band_mode = 0;                 // 0 auto (when M is banded), 1 never
+    int band_B_req = 0, band_ov_req = 0;   // 0: defaults
+    bool band = false;
+    int band_bw = -1, band_B = 0, band_ov = 0, band_steps = 0, band_ngroup = 0;
+    double *band_Lrow = nullptr, *band_L = nullptr, *band_y = nullptr;
+    int *band_ok = nullptr;
 };
 
 struct ipb_ctx {
@@ -339,7 +346,7 @@ extern "C" int ipb_ctx_create(int device, ipb_ctx **out) {
     if (env && atoi(env) > 0) per_sm = std::min(occ, atoi(env));
     ctx->blocks = std::min(MAX_GRID, per_sm * ctx->sms);
     CHECK(dalloc(ctx, &ctx->barrier, 1));
-    CHECK(dalloc(ctx, &ctx->partials, (size_t)NSLOT * MAX_GRID));
+    CHECK(dalloc(ctx, &ctx->partials, (size_t)2 * NSLOT * MAX_GRID));
     CHECK(dalloc(ctx, &ctx->abort_flag, 1));
     CU(ctx, cudaMemset(ctx->barrier, 0, sizeof(unsigned)));
     CU(ctx, cudaMemset(ctx->abort_flag, 0, sizeof(int)));
@@ -784,6 +791,88 @@ static int build_aat_pattern(ipb_ctx *ctx, ipb_proj *p) {
     return status;
 }
 
+// ------------------------------------------------------------------ banded factor of M
+static void free_band(ipb_proj *p) {
+    cudaFree(p->band_Lrow); cudaFree(p->band_L); cudaFree(p->band_y); cudaFree(p->band_ok);
+    p->band_Lrow = p->band_L = p->band_y = nullptr; p->band_ok = nullptr;
+    p->band = false; p->band_bw = -1; p->band_ngroup = 0;
+}
+
+// Decide whether M is banded (half-bandwidth < HB) and size the chunked
+// factor: B owned rows per chunk such that the machine gets ~8 groups of 32
+// chunks per SM (enough bulk copies in flight to saturate HBM) without the
+// overlap (ov rows each side, read redundantly) dominating.
+static int build_band(ipb_ctx *ctx, ipb_proj *p) {
+    free_band(p);
+    if (p->parts || !p->has_M || p->band_mode == 1 || p->m < 1) return IPB_OK;
+    const int m = (int)p->m;
+    int *d_bw = nullptr;
+    CHECK(dalloc(ctx, &d_bw, 1));
+    CU(ctx, cudaMemsetAsync(d_bw, 0, sizeof(int), ctx->stream));
+    k_band_width<<<cdiv(m, 256), 256, 0, ctx->stream>>>(m, p->m_rowptr, p->m_col, d_bw);
+    ctx->launches += 1;
+    int bw = 0;
+    CU(ctx, cudaMemcpyAsync(&bw, d_bw, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bw);
+    p->band_bw = bw;
+    if (bw < 1 || bw >= HB) return IPB_OK;      // diagonal M: CG takes one step; wide M: CG
+    int ov = p->band_ov_req > 0 ? p->band_ov_req : 48;
+    ov = (ov + 3) & ~3;
+    int B = p->band_B_req;
+    if (B <= 0) {
+        const int64_t groups = 8 * (int64_t)ctx->sms;
+        B = (int)((m + 32 * groups - 1) / (32 * groups));
+        B = std::max(32, std::min(512, B));
+    }
+    B = (B + 3) & ~3;
+    const int64_t nchunk = (m + (int64_t)B - 1) / B;
+    const int64_t ngroup = (nchunk + 31) / 32;
+    p->band_B = B; p->band_ov = ov; p->band_steps = B + 2 * ov; p->band_ngroup = (int)ngroup;
+    CHECK(dalloc(ctx, &p->band_Lrow, (size_t)m * HB));
+    CHECK(dalloc(ctx, &p->band_L, (size_t)ngroup * p->band_steps * HB * 32));
+    CHECK(dalloc(ctx, &p->band_y, (size_t)ngroup * (B + ov) * 32));
+    CHECK(dalloc(ctx, &p->band_ok, 1));
+    p->band = true;
+    return IPB_OK;
+}
+
+static int refresh_band(ipb_ctx *ctx, ipb_proj *p) {
+    if (!p->band) return IPB_OK;
+    const int m = (int)p->m, B = p->band_B;
+    const int one = 1;
+    CU(ctx, cudaMemcpyAsync(p->band_ok, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t nchunk = (m + (int64_t)B - 1) / B;
+    k_band_factor<<<cdiv(nchunk, 64), 64, 0, ctx->stream>>>(m, p->m_rowptr, p->m_col, p->m_val, B,
+                                                            48, p->band_Lrow, p->band_ok);
+    const long long total = (long long)p->band_ngroup * p->band_steps * HB * 32;
+    k_band_interleave<<<cdiv(total, 256), 256, 0, ctx->stream>>>(m, B, p->band_ov, p->band_steps,
+                                                                 total, p->band_Lrow, p->band_L);
+    ctx->launches += 2;
+    return IPB_OK;
+}
+
+extern "C" int ipb_proj_set_band(ipb_ctx *ctx, ipb_proj *p, int mode, int chunk_rows, int overlap) {
+    if (!ctx || !p || mode < 0 || mode > 1 || chunk_rows < 0 || overlap < 0) return IPB_ERR_INVALID;
+    p->band_mode = mode; p->band_B_req = chunk_rows; p->band_ov_req = overlap;
+    CHECK(build_band(ctx, p));
+    CHECK(refresh_band(ctx, p));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+extern "C" int ipb_proj_band_info(ipb_ctx *ctx, const ipb_proj *p, int32_t *out) {
+    if (!ctx || !p || !out) return IPB_ERR_INVALID;
+    int ok = 0;
+    if (p->band) {
+        CU(ctx, cudaMemcpyAsync(&ok, p->band_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    out[0] = p->band ? 1 : 0; out[1] = p->band_bw; out[2] = p->band_B; out[3] = p->band_ov;
+    out[4] = p->band_ngroup; out[5] = ok;
+    return IPB_OK;
+}
+
 extern "C" int ipb_proj_refresh(ipb_ctx *ctx, ipb_proj *p) {
     if (!ctx || !p) return IPB_ERR_INVALID;
     if (p->parts) return IPB_OK;       // the host supplies refreshed parts
@@ -803,6 +892,7 @@ extern "C" int ipb_proj_refresh(ipb_ctx *ctx, ipb_proj *p) {
             k_aat_values<<<cdiv(A->rows, 128), 128, 0, ctx->stream>>>(
                 A->rows, A->rowptr, A->col, p->nval, p->m_rowptr, p->m_col, p->m_val);
             ctx->launches += 1;
+            CHECK(refresh_band(ctx, p));
         }
         CHECK(device_sum(ctx, p->dnorm2, A->rows, &s));
     }
@@ -840,6 +930,11 @@ extern "C" int ipb_proj_create(ipb_ctx *ctx, ipb_csr *A, double orth_tol, int ma
     const char *env = getenv("IPB_EXPLICIT_AAT");      // 0 auto, 1 never, 2 always
     if (env) p->aat_mode = atoi(env);
     CHECK(build_aat_pattern(ctx, p));
+    const char *benv = getenv("IPB_BAND");             // 0: never use the banded factor
+    if (benv && atoi(benv) == 0) p->band_mode = 1;
+    if ((benv = getenv("IPB_BAND_B"))) p->band_B_req = atoi(benv);
+    if ((benv = getenv("IPB_BAND_OV"))) p->band_ov_req = atoi(benv);
+    CHECK(build_band(ctx, p));
     CHECK(ipb_proj_refresh(ctx, p));
     *out = p;
     return IPB_OK;
@@ -850,6 +945,7 @@ extern "C" int ipb_proj_set_aat_mode(ipb_ctx *ctx, ipb_proj *p, int mode) {
     if (p->parts) IPB_FAIL(ctx, IPB_ERR_INVALID, "a projector built from parts holds M iff it was given");
     p->aat_mode = mode;
     CHECK(build_aat_pattern(ctx, p));
+    CHECK(build_band(ctx, p));
     return ipb_proj_refresh(ctx, p);
 }
 
@@ -864,6 +960,7 @@ extern "C" int ipb_proj_destroy(ipb_ctx *ctx, ipb_proj *p) {
     vfree(ctx, p->v); vfree(ctx, p->r); vfree(ctx, p->w); vfree(ctx, p->p); vfree(ctx, p->s);
     vfree(ctx, p->rhs); vfree(ctx, p->t);
     free_aat(p);
+    free_band(p);
     delete p;
     return IPB_OK;
 }
@@ -876,6 +973,11 @@ static ProjView proj_view(const ipb_proj *p) {
     v.fro = p->fro; v.orth_tol = p->orth_tol; v.max_refin = p->max_refin;
     v.rtol = p->rtol; v.maxit = p->maxit;
     v.v = p->v; v.r = p->r; v.w = p->w; v.p = p->p; v.s = p->s; v.rhs = p->rhs; v.t = p->t;
+    if (p->band) {
+        v.band.enabled = 1; v.band.B = p->band_B; v.band.ov = p->band_ov;
+        v.band.steps = p->band_steps; v.band.ngroup = p->band_ngroup;
+        v.band.L = p->band_L; v.band.y = p->band_y; v.band.ok = p->band_ok;
+    }
     if (p->parts) {
         v.A = csr_view(p->pA_norm);
         v.At = csr_view(p->pAt_norm);
@@ -919,7 +1021,7 @@ static int run_proj(ipb_ctx *ctx, ipb_proj *p, int op, const double *din, double
     if (info) {
         info->inner_iters = h->inner_iters; info->n_solves = h->n_solves;
         info->n_refinements = h->n_refinements; info->status = h->status;
-        info->reserved = 0; info->orth = h->orth; info->kernel_ms = ms;
+        info->n_fallbacks = h->n_fallbacks; info->orth = h->orth; info->kernel_ms = ms;
     }
     if (h->status != 0)
         IPB_FAIL(ctx, h->status, "inner CG on A A' broke down (status %d)", h->status);
@@ -990,7 +1092,7 @@ extern "C" int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_v
 }
 
 extern "C" int ipb_bench_phase(ipb_ctx *ctx, ipb_proj *p, int phase, int reps, double *ms) {
-    if (!ctx || !p || reps <= 0 || phase < 0 || phase > 8) return IPB_ERR_INVALID;
+    if (!ctx || !p || reps <= 0 || phase < 0 || phase > 9) return IPB_ERR_INVALID;
     ipb_proj_info info;
     CHECK(run_proj(ctx, p, 10 + phase, p->rhs, nullptr, reps, &info));
     if (ms) *ms = info.kernel_ms;
@@ -1148,7 +1250,7 @@ extern "C" int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b, d
     if (info) {
         info->inner_iters = h->inner_iters; info->n_solves = h->n_solves;
         info->n_refinements = h->n_refinements; info->status = h->status;
-        info->reserved = 0; info->orth = 0.0; info->kernel_ms = ms;
+        info->n_fallbacks = h->n_fallbacks; info->orth = 0.0; info->kernel_ms = ms;
     }
     if (h->status != 0)
         IPB_FAIL(ctx, h->status, "modified dogleg: inner solve failed (status %d)", h->status);

@@ -36,7 +36,7 @@ class PcgInfo(C.Structure):
 class ProjInfo(C.Structure):
     _fields_ = [("inner_iters", C.c_int64), ("n_solves", C.c_int64),
                 ("n_refinements", C.c_int64), ("status", C.c_int32),
-                ("reserved", C.c_int32), ("orth", C.c_double),
+                ("n_fallbacks", C.c_int32), ("orth", C.c_double),
                 ("kernel_ms", C.c_double)]
 
 
@@ -74,6 +74,8 @@ PROTOTYPES = {
     "ipb_proj_refresh": (C.c_int, [_P, _P]),
     "ipb_proj_set_aat_mode": (C.c_int, [_P, _P, C.c_int]),
     "ipb_proj_aat_nnz": (_I64, [_P]),
+    "ipb_proj_set_band": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
+    "ipb_proj_band_info": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "ipb_bench_phase": (C.c_int, [_P, _P, C.c_int, C.c_int, _D]),
     "ipb_proj_destroy": (C.c_int, [_P, _P]),
     "ipb_proj_null_space": (C.c_int, [_P, _P, _D, _D, C.POINTER(ProjInfo)]),

@@ -240,20 +240,24 @@ class DeviceProjector:
     device.  Holds the device copy of A (and A')."""
 
     def __init__(self, ctx, A, orth_tol=1e-12, max_refin=3, inner_rtol=1e-13,
-                 inner_maxit=1000, aat_mode=0):
+                 inner_maxit=1000, aat_mode=0, band=(0, 0, 0)):
         self.ctx = ctx
         self.A = A if isinstance(A, DeviceCSR) else DeviceCSR(ctx, A, True)
         self.m, self.n = self.A.shape
+        band = tuple(int(v) for v in band)
         self.params = (float(orth_tol), int(max_refin), float(inner_rtol),
-                       int(inner_maxit), int(aat_mode))
+                       int(inner_maxit), int(aat_mode), band)
         h = C.c_void_p()
         ctx.check(ctx.lib.ipb_proj_create(ctx.h, self.A.h, *self.params[:4], C.byref(h)))
         self.h = h
         weakref.finalize(self, ctx.lib.ipb_proj_destroy, ctx.h, h)
         if aat_mode:
             self.set_aat_mode(aat_mode)
+        if band != (0, 0, 0):
+            self.set_band(*band)
         self.last_info = None
-        self.totals = dict(inner_iters=0, n_solves=0, n_refinements=0, applies=0)
+        self.totals = dict(inner_iters=0, n_solves=0, n_refinements=0, applies=0,
+                           n_fallbacks=0)
 
     def refresh(self):
         self.ctx.check(self.ctx.lib.ipb_proj_refresh(self.ctx.h, self.h))
@@ -262,6 +266,20 @@ class DeviceProjector:
         """0: explicit A A' when it moves fewer bytes (default), 1: always
         A then A', 2: always the explicit product."""
         self.ctx.check(self.ctx.lib.ipb_proj_set_aat_mode(self.ctx.h, self.h, int(mode)))
+
+    def set_band(self, mode=0, chunk_rows=0, overlap=0):
+        """Banded direct solve of ``(A A')``: mode 0 use it when ``A A'`` is
+        banded (default), 1 never (CG only); chunk_rows / overlap 0 = defaults."""
+        self.ctx.check(self.ctx.lib.ipb_proj_set_band(
+            self.ctx.h, self.h, int(mode), int(chunk_rows), int(overlap)))
+
+    @property
+    def band_info(self):
+        """dict(in_use, bandwidth, chunk_rows, overlap, groups, trusted)."""
+        out = (C.c_int32 * 6)()
+        self.ctx.check(self.ctx.lib.ipb_proj_band_info(self.ctx.h, self.h, out))
+        return dict(zip(("in_use", "bandwidth", "chunk_rows", "overlap", "groups", "trusted"),
+                        [int(v) for v in out]))
 
     @property
     def aat_nnz(self):
@@ -273,6 +291,7 @@ class DeviceProjector:
         self.totals["inner_iters"] += info.inner_iters
         self.totals["n_solves"] += info.n_solves
         self.totals["n_refinements"] += info.n_refinements
+        self.totals["n_fallbacks"] += info.n_fallbacks
         self.totals["applies"] += 1
 
     def null_space(self, x):

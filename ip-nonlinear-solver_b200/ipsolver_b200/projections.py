@@ -24,7 +24,10 @@ DENSE_METHODS = ("QRFactorization", "SVDFactorization")
 # ``aat_mode``: 0 keep the explicit product A A' in HBM when that moves fewer
 # bytes per inner iteration (default), 1 always apply A' then A, 2 always
 # use the explicit product.
-_INNER = {"inner_rtol": 1e-13, "inner_maxit": 1000, "aat_mode": 0}
+# ``band``: (mode, chunk_rows, overlap) of the banded direct solve -- mode 0
+# factorises A A' when it is banded and solves by substitution sweeps (CG only
+# as the fallback), mode 1 never does; 0 for the sizes = defaults.
+_INNER = {"inner_rtol": 1e-13, "inner_maxit": 1000, "aat_mode": 0, "band": (0, 0, 0)}
 
 
 def set_inner_options(**kw):
@@ -103,7 +106,8 @@ def _binding_for(A, orth_tol, max_refin):
     key = (A.shape, A.nnz)
     cached = ctx._pattern_cache.get(key)
     params = (float(orth_tol), int(max_refin), float(_INNER["inner_rtol"]),
-              int(_INNER["inner_maxit"]), int(_INNER["aat_mode"]))
+              int(_INNER["inner_maxit"]), int(_INNER["aat_mode"]),
+              tuple(int(v) for v in _INNER["band"]))
     if cached is not None and cached.params == params and cached.A.same_pattern(A):
         cached.A.update_values(A.data)
         cached.refresh()

@@ -218,3 +218,14 @@ PROBLEMS = {
     "thomson_20_equals": _thomson(20, "equals", "equality_constrained_sqp"),
     "thomson_20_less": _thomson(20, "less", "tr_interior_point"),
 }
+
+# BASELINE.json configs 2-4 at their stated sizes (golden records: a strided
+# sample of x / v plus norms, tests/golden/make_golden_large.py -> e2e_large.npz)
+LARGE_PROBLEMS = {
+    "eqp_window_1000000": _eqp(1000000, "window"),
+    "ipqp_window_1000000": _ipqp(1000000),
+    "ipqp_window_100000": _ipqp(100000),
+    "thomson_2000_equals": _thomson(2000, "equals", "equality_constrained_sqp"),
+    "thomson_500_equals": _thomson(500, "equals", "equality_constrained_sqp"),
+}
+LARGE_STRIDE = 997       # sample x[::LARGE_STRIDE], v[::LARGE_STRIDE]

@@ -20,12 +20,14 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-8
 
 
-# every test runs with both representations of (A A') in the inner CG:
-# A then A' (two SpMVs) and the explicit product M = A A' (one SpMV)
-@pytest.fixture(scope="module", params=[1, 2], ids=["AtA", "explicitM"])
+# every test runs with the three ways (A A')^-1 is applied: CG with A then A'
+# (two SpMVs), CG with the explicit product M = A A' (one SpMV), and the banded
+# direct solve (used when M is banded; the CG on M otherwise / as its fallback)
+@pytest.fixture(scope="module", params=[(1, 1), (2, 1), (2, 0)],
+                ids=["cgAtA", "cgM", "band"])
 def dev(request):
     from ipsolver_b200 import device, projections, qp_subproblem
-    projections.set_inner_options(aat_mode=request.param)
+    projections.set_inner_options(aat_mode=request.param[0], band=(request.param[1], 0, 0))
 
     class NS:
         pass
@@ -36,7 +38,7 @@ def dev(request):
     ns.orthogonality = projections.orthogonality
     ns.qp = qp_subproblem
     yield ns
-    projections.set_inner_options(aat_mode=0)
+    projections.set_inner_options(aat_mode=0, band=(0, 0, 0))
 
 
 @pytest.fixture(scope="module")
