@@ -250,6 +250,17 @@ int ipb_proj_create_parts(ipb_ctx *ctx, ipb_csr *A_raw, ipb_csr *A_norm, ipb_csr
                           double orth_tol, int max_refin, double inner_rtol, int inner_maxit,
                           ipb_proj **out);
 
+/* Banded direct solve for a projector made from parts (see ipb_proj_set_band):
+ * M_ext = rows [own_lo - ext_off, own_hi + margin) of M = A~ A~' as a standalone
+ * square CSR (created with_transpose = 0; columns relative to its first row,
+ * entries outside dropped).  The margins (>= overlap + 48 rows where the matrix
+ * has them) let the factor recurrence forget its truncated start.  ghost_below /
+ * ghost_above (<= overlap): rows of the neighbours the sweeps read next to the
+ * own block -- the m-space ghost zones passed to ipb_comm_init must hold exactly
+ * these rows, contiguously. */
+int ipb_proj_set_band_parts(ipb_ctx *ctx, ipb_proj *p, const ipb_csr *M_ext, int64_t ext_off,
+                            int ghost_below, int ghost_above, int chunk_rows, int overlap);
+
 /* ---- device vectors ------------------------------------------------------ */
 int ipb_vec_create(ipb_ctx *ctx, int64_t len, ipb_vec **out);
 int ipb_vec_destroy(ipb_ctx *ctx, ipb_vec *v);
@@ -275,6 +286,14 @@ int ipb_timer_stop(ipb_ctx *ctx, double *ms);
  * dominant loop of the path, timed in isolation. */
 int ipb_bench_inner_iterations(ipb_ctx *ctx, ipb_proj *p, const ipb_vec *x,
                                int iters, double *ms);
+
+/* Barrier timeline: with capacity > 0 every following launch records the
+ * %globaltimer (ns) at which CTA 0 leaves each grid barrier; ipb_trace_read
+ * returns the stamps of the LAST launch (count = barriers passed, of which at
+ * most ``capacity`` are stored).  Consecutive differences are the durations of
+ * the phases inside the persistent kernel.  capacity = 0 switches it off. */
+int ipb_trace_enable(ipb_ctx *ctx, int capacity);
+int ipb_trace_read(ipb_ctx *ctx, uint64_t *out, int capacity, int *count);
 
 /* Repeats ONE phase of the inner iteration ``reps`` times inside one launch,
  * a grid barrier after each (0: fused vector update, 1: A' r, 2: A t, 3: M r,

@@ -74,6 +74,7 @@ struct ipb_proj {
     int band_bw = -1, band_B = 0, band_ov = 0, band_steps = 0, band_ngroup = 0;
     double *band_Lrow = nullptr, *band_L = nullptr, *band_y = nullptr;
     int *band_ok = nullptr;
+    int band_in_lo = 0, band_in_hi = 0;   // rows of a sweep's input that exist (own-relative)
 };
 
 struct ipb_ctx {
@@ -95,6 +96,8 @@ struct ipb_ctx {
     size_t cub_tmp_bytes = 0;
     int64_t launches = 0;
     std::string err;
+    unsigned long long *trace = nullptr;   // barrier timeline of the next launches (ipb_trace_*)
+    int trace_cap = 0;
     // ---- multi-GPU (ipb_comm_*): symmetric arena + peer mappings
     int rank = 0, size = 1;
     char *arena = nullptr;             // [mailbox | flags | seq | vectors]
@@ -158,6 +161,7 @@ static SyncView sync_view(const ipb_ctx *ctx) {
     s.barrier = ctx->barrier;
     s.partials = ctx->partials;
     s.abort_flag = ctx->abort_flag;
+    s.trace = ctx->trace; s.trace_cap = ctx->trace_cap;
     s.C.rank = ctx->rank; s.C.size = ctx->size;
     if (ctx->size > 1) {
         s.C.arena = (double *)ctx->arena;
@@ -271,6 +275,7 @@ template <typename Args>
 static int launch_coop(ipb_ctx *ctx, void (*kernel)(const Args), const Args &args,
                        int grid, float *ms) {
     CU(ctx, cudaMemsetAsync(ctx->barrier, 0, sizeof(unsigned), ctx->stream));
+    if (ctx->trace) CU(ctx, cudaMemsetAsync(ctx->trace, 0, sizeof(unsigned long long), ctx->stream));
     void *params[] = {(void *)&args};
     if (ms) CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CU(ctx, cudaLaunchCooperativeKernel((void *)kernel, dim3(grid), dim3(THREADS),
@@ -361,7 +366,7 @@ extern "C" int ipb_ctx_destroy(ipb_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->barrier); cudaFree(ctx->partials); cudaFree(ctx->abort_flag);
     cudaFree(ctx->d_result); cudaFreeHost(ctx->h_result);
-    cudaFree(ctx->ws); cudaFree(ctx->stage); cudaFree(ctx->cub_tmp);
+    cudaFree(ctx->ws); cudaFree(ctx->stage); cudaFree(ctx->cub_tmp); cudaFree(ctx->trace);
     for (int q = 0; q < ctx->size; ++q)
         if (q != ctx->rank && ctx->peer_base[q]) cudaIpcCloseMemHandle(ctx->peer_base[q]);
     cudaFree(ctx->arena); cudaFree(ctx->send_ent[0]); cudaFree(ctx->send_ent[1]);
@@ -407,6 +412,30 @@ extern "C" int ipb_timer_stop(ipb_ctx *ctx, double *ms) {
     CU(ctx, cudaEventSynchronize(ctx->ev3));
     CU(ctx, cudaEventElapsedTime(&f, ctx->ev2, ctx->ev3));
     *ms = f;
+    return IPB_OK;
+}
+
+// ------------------------------------------------------------------ barrier timeline
+extern "C" int ipb_trace_enable(ipb_ctx *ctx, int capacity) {
+    if (!ctx || capacity < 0) return IPB_ERR_INVALID;
+    cudaFree(ctx->trace);
+    ctx->trace = nullptr; ctx->trace_cap = 0;
+    if (capacity > 0) {
+        CHECK(dalloc(ctx, &ctx->trace, (size_t)capacity + 1));
+        CU(ctx, cudaMemset(ctx->trace, 0, ((size_t)capacity + 1) * sizeof(unsigned long long)));
+        ctx->trace_cap = capacity + 1;
+    }
+    return IPB_OK;
+}
+extern "C" int ipb_trace_read(ipb_ctx *ctx, uint64_t *out, int capacity, int *count) {
+    if (!ctx || !out || !count || !ctx->trace) return IPB_ERR_INVALID;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long k = 0;
+    CU(ctx, cudaMemcpy(&k, ctx->trace, sizeof k, cudaMemcpyDeviceToHost));
+    const int have = (int)std::min<unsigned long long>(k, (unsigned long long)std::min(capacity, ctx->trace_cap - 1));
+    if (have > 0)
+        CU(ctx, cudaMemcpy(out, ctx->trace + 1, (size_t)have * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    *count = (int)k;
     return IPB_OK;
 }
 
@@ -821,9 +850,9 @@ static int build_band(ipb_ctx *ctx, ipb_proj *p) {
     ov = (ov + 3) & ~3;
     int B = p->band_B_req;
     if (B <= 0) {
-        const int64_t groups = 8 * (int64_t)ctx->sms;
+        const int64_t groups = 6 * (int64_t)ctx->sms;
         B = (int)((m + 32 * groups - 1) / (32 * groups));
-        B = std::max(32, std::min(512, B));
+        B = std::max(64, std::min(512, B));
     }
     B = (B + 3) & ~3;
     const int64_t nchunk = (m + (int64_t)B - 1) / B;
@@ -833,6 +862,7 @@ static int build_band(ipb_ctx *ctx, ipb_proj *p) {
     CHECK(dalloc(ctx, &p->band_L, (size_t)ngroup * p->band_steps * HB * 32));
     CHECK(dalloc(ctx, &p->band_y, (size_t)ngroup * (B + ov) * 32));
     CHECK(dalloc(ctx, &p->band_ok, 1));
+    p->band_in_lo = 0; p->band_in_hi = m;
     p->band = true;
     return IPB_OK;
 }
@@ -847,7 +877,7 @@ static int refresh_band(ipb_ctx *ctx, ipb_proj *p) {
                                                             48, p->band_Lrow, p->band_ok);
     const long long total = (long long)p->band_ngroup * p->band_steps * HB * 32;
     k_band_interleave<<<cdiv(total, 256), 256, 0, ctx->stream>>>(m, B, p->band_ov, p->band_steps,
-                                                                 total, p->band_Lrow, p->band_L);
+                                                                 total, 0, p->band_Lrow, p->band_L);
     ctx->launches += 2;
     return IPB_OK;
 }
@@ -858,6 +888,68 @@ extern "C" int ipb_proj_set_band(ipb_ctx *ctx, ipb_proj *p, int mode, int chunk_
     CHECK(build_band(ctx, p));
     CHECK(refresh_band(ctx, p));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+// Row-partitioned projector: the banded factor of the rank's own rows of M.
+// M_ext holds rows [own_lo - ext_off, ...) of M as a standalone square CSR
+// (columns relative to its first row, entries outside dropped): the own rows
+// plus a margin on each side, so that the factor recurrence, started at the
+// margin's edge, has forgotten its start where the sweeps use it.  The sweeps
+// read ghost_below / ghost_above rows of their input beyond the own block:
+// the m-space ghost zones must hold exactly those rows (contiguous).
+extern "C" int ipb_proj_set_band_parts(ipb_ctx *ctx, ipb_proj *p, const ipb_csr *M_ext,
+                                       int64_t ext_off, int ghost_below, int ghost_above,
+                                       int chunk_rows, int overlap) {
+    if (!ctx || !p || !p->parts || !M_ext || ext_off < 0 || ghost_below < 0 || ghost_above < 0 ||
+        chunk_rows < 0 || overlap < 0)
+        return IPB_ERR_INVALID;
+    free_band(p);
+    const int m = (int)p->m, m_ext = M_ext->rows;
+    if (m < 1) return IPB_OK;
+    if (!p->pM) IPB_FAIL(ctx, IPB_ERR_INVALID, "the banded solve needs the own rows of M (residual check)");
+    int ov = overlap > 0 ? overlap : 48;
+    ov = (ov + 3) & ~3;
+    if (ghost_below > ov || ghost_above > ov || ext_off < ghost_below || ext_off + m + ghost_above > m_ext)
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "ipb_proj_set_band_parts: margins do not cover the ghost rows");
+    if (ctx->size > 1 && (ghost_below > ctx->n_lo[1] || ghost_above > ctx->n_hi[1]))
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "m-space ghost zones are smaller than the sweep's halo");
+    int *d_bw = nullptr;
+    CHECK(dalloc(ctx, &d_bw, 1));
+    CU(ctx, cudaMemsetAsync(d_bw, 0, sizeof(int), ctx->stream));
+    k_band_width<<<cdiv(m_ext, 256), 256, 0, ctx->stream>>>(m_ext, M_ext->rowptr, M_ext->col, d_bw);
+    int bw = 0;
+    CU(ctx, cudaMemcpyAsync(&bw, d_bw, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bw);
+    p->band_bw = bw;
+    if (bw < 1 || bw >= HB) return IPB_OK;
+    int B = chunk_rows;
+    if (B <= 0) {
+        const int64_t groups = 6 * (int64_t)ctx->sms;
+        B = (int)((m + 32 * groups - 1) / (32 * groups));
+        B = std::max(64, std::min(512, B));
+    }
+    B = (B + 3) & ~3;
+    const int64_t nchunk = (m + (int64_t)B - 1) / B;
+    const int64_t ngroup = (nchunk + 31) / 32;
+    p->band_B = B; p->band_ov = ov; p->band_steps = B + 2 * ov; p->band_ngroup = (int)ngroup;
+    CHECK(dalloc(ctx, &p->band_Lrow, (size_t)m_ext * HB));
+    CHECK(dalloc(ctx, &p->band_L, (size_t)ngroup * p->band_steps * HB * 32));
+    CHECK(dalloc(ctx, &p->band_y, (size_t)ngroup * (B + ov) * 32));
+    CHECK(dalloc(ctx, &p->band_ok, 1));
+    const int one = 1;
+    CU(ctx, cudaMemcpyAsync(p->band_ok, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const int FB = 128;       // rows per factor thread
+    k_band_factor<<<cdiv(cdiv(m_ext, FB), 64), 64, 0, ctx->stream>>>(
+        m_ext, M_ext->rowptr, M_ext->col, M_ext->val, FB, 48, p->band_Lrow, p->band_ok);
+    const long long total = (long long)ngroup * p->band_steps * HB * 32;
+    k_band_interleave<<<cdiv(total, 256), 256, 0, ctx->stream>>>(m_ext, B, ov, p->band_steps, total,
+                                                                 (long long)ext_off, p->band_Lrow, p->band_L);
+    ctx->launches += 3;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    p->band_in_lo = -ghost_below; p->band_in_hi = m + ghost_above;
+    p->band = true;
     return IPB_OK;
 }
 
@@ -977,6 +1069,7 @@ static ProjView proj_view(const ipb_proj *p) {
         v.band.enabled = 1; v.band.B = p->band_B; v.band.ov = p->band_ov;
         v.band.steps = p->band_steps; v.band.ngroup = p->band_ngroup;
         v.band.L = p->band_L; v.band.y = p->band_y; v.band.ok = p->band_ok;
+        v.band.in_lo = p->band_in_lo; v.band.in_hi = p->band_in_hi;
     }
     if (p->parts) {
         v.A = csr_view(p->pA_norm);

@@ -117,6 +117,8 @@ struct SyncView {
     unsigned *barrier;        // sense-reversing arrival counter
     double *partials;         // [2][NSLOT][MAX_GRID], double-buffered by barrier parity
     int *abort_flag;          // set when a spin times out
+    unsigned long long *trace;  // optional: [0] = count, then the %globaltimer of every
+    int trace_cap;              // grid barrier as CTA 0 leaves it (phase timeline, ns)
     CommView C;
 };
 
@@ -130,12 +132,14 @@ struct SyncView {
 // (a "group") per warp; the factor rows of a group are stored interleaved,
 // [step][k][lane], so that a step of a warp is one contiguous 2 KB block.
 constexpr int HB = 8;             // doubles per factor row: 1/L_ii, L[i][i-1..i-7]
-constexpr int BAND_NBUF = 4;      // per-warp ring of step buffers (TMA bulk copies)
-static_assert(HB == 8 && BAND_NBUF == 4, "k_band_interleave and Smem::bfull assume these");
+static_assert(HB == 8, "k_band_interleave assumes 256 doubles per step");
 struct BandView {
     int enabled;
     int B, ov, steps;             // owned rows per chunk, overlap, steps = B + 2 ov (multiples of 4)
     int ngroup;                   // groups of 32 chunks
+    int in_lo, in_hi;             // rows of a sweep's input that exist, own-relative: [0, m) on one
+                                  // GPU; a row-partitioned rank also reads up to ov ghost rows of its
+                                  // neighbours on each side (rows outside read as 0)
     const double *L;              // [ngroup][steps][HB][32]
     double *y;                    // [ngroup][B + ov][32]: forward result kept for the backward sweep
     int *ok;                      // 1 while the factor is trusted (0: breakdown / no contraction seen)
@@ -226,6 +230,13 @@ __device__ __forceinline__ void grid_sync(const SyncView &S, Smem &sm) {
             if (++spins > (1ll << 31)) { *S.abort_flag = 1; __trap(); }
         } while (((old ^ cur) & 0x80000000u) == 0);
         bump_phase(sm);
+        if (S.trace && blockIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            const unsigned long long k = S.trace[0];
+            if ((long long)k + 1 < S.trace_cap) S.trace[k + 1] = t;
+            S.trace[0] = k + 1;
+        }
     }
     __syncthreads();
 }
@@ -282,7 +293,7 @@ struct __align__(128) Smem {
     unsigned gseq;                // cross-GPU sequence number (multi-GPU only)
     unsigned ghost_seq;           // sequence number the ghost zone of the current product carries
     unsigned phase;               // grid barriers passed so far (parity selects the partials buffer)
-    unsigned long long bfull[WARPS][4];   // banded sweep: per-warp ring of factor-row buffers
+    unsigned long long bfull[WARPS * 4];  // banded sweep: mbarriers of the per-warp rings of step buffers
     unsigned bseq[WARPS];         // ring uses of each warp so far
     double red[WARPS];
     double out[NSLOT];
@@ -338,11 +349,9 @@ __device__ __forceinline__ void pipeline_init(Smem &sm, const SyncView &S) {
         }
         sm.seq = 0;
         sm.phase = 0;
-        for (int w = 0; w < WARPS; ++w) {
-            sm.bseq[w] = 0;
-            for (int q = 0; q < 4; ++q)
-                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.bfull[w][q])));
-        }
+        for (int w = 0; w < WARPS; ++w) sm.bseq[w] = 0;
+        for (int q = 0; q < WARPS * 4; ++q)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.bfull[q])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -818,68 +827,64 @@ __device__ __forceinline__ void set_ops(Smem &sm, int o0, int o1 = 0, int o2 = 0
     __syncthreads();
 }
 
-// ---------------------------------------------------------------- fused CG update
-// p = r + beta p;  s = w + beta s;  v += alpha p;  r -= alpha s;  returns this
-// thread's share of r.r -- the one vector pass of the inner iteration
-// (5 reads + 4 writes of m-vectors).  It runs as a TMA pipeline through the
-// same shared-memory stages as the SpMV: tiles of UT entries of the five
-// vectors come in by bulk copies, are updated in place in shared memory and
-// go out by bulk stores (cp.async.bulk.global.shared::cta), so the pass does
-// not depend on L1 (almost none is left next to the stages) and keeps deep
-// queues of reads and writes in flight.
-constexpr int UT = (int)((sizeof(Stage) / (5 * sizeof(double))) & ~(size_t)31);
-
+// ---------------------------------------------------------------- streaming passes
+// Elementwise pass over NV vectors of length ``len`` as a TMA pipeline through
+// the same shared-memory stages as the SpMV: tiles of TS entries of the NV
+// input vectors come in by bulk copies, ``f(t, e)`` updates entry e of the
+// tiles in place (t[k * TS + e] is vector k) and the tiles k with out[k] != 0
+// leave by bulk stores (cp.async.bulk.global.shared::cta).  The pass does not
+// depend on L1 (almost none is left next to the stages: a register-path
+// version of the CG update reached 80 % of the copy bandwidth, this one 90 %)
+// and keeps deep queues of reads and writes in flight.  in[k] / out[k] must be
+// 16-byte aligned with one entry of slack behind ``len``.
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(dst), "r"(smem_addr(src)), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ void update_issue(const ProjView &P, Smem &sm, int s, int t0, int cnt) {
+template <int NV>
+struct TileIO {
+    const double *in[NV];
+    double *out[NV];
+};
+
+template <int NV>
+__device__ __forceinline__ void tile_issue(const TileIO<NV> &io, Smem &sm, int s, int t0, int cnt) {
+    constexpr int TS = (int)((sizeof(Stage) / (NV * sizeof(double))) & ~(size_t)31);
     double *buf = reinterpret_cast<double *>(&sm.st[s]);
     const unsigned bytes = (unsigned)(((cnt + 1) & ~1) * 8);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                 ::"r"(smem_addr(&sm.full[s])), "r"(5u * bytes) : "memory");
-    bulk_g2s(buf + 0 * UT, P.r + t0, bytes, &sm.full[s]);
-    bulk_g2s(buf + 1 * UT, P.w + t0, bytes, &sm.full[s]);
-    bulk_g2s(buf + 2 * UT, P.p + t0, bytes, &sm.full[s]);
-    bulk_g2s(buf + 3 * UT, P.s + t0, bytes, &sm.full[s]);
-    bulk_g2s(buf + 4 * UT, P.v + t0, bytes, &sm.full[s]);
+                 ::"r"(smem_addr(&sm.full[s])), "r"((unsigned)NV * bytes) : "memory");
+#pragma unroll
+    for (int k = 0; k < NV; ++k) bulk_g2s(buf + k * TS, io.in[k] + t0, bytes, &sm.full[s]);
 }
 
-__device__ __noinline__ double cg_update(const ProjView &P, Smem &sm, const SyncView &S,
-                                         double alpha, double beta) {
+template <int NV, class F>
+__device__ __forceinline__ void tile_pass(Smem &sm, const SyncView &S, int len,
+                                          const TileIO<NV> &io, F &&f) {
+    constexpr int TS = (int)((sizeof(Stage) / (NV * sizeof(double))) & ~(size_t)31);
     const int tid = threadIdx.x;
-    const int m = P.m;
-    double gpart = 0.0;
     __syncthreads();
-    const int ntile = (m + UT - 1) / UT;
+    const int ntile = (len + TS - 1) / TS;
     const int per = (ntile + (int)gridDim.x - 1) / (int)gridDim.x;
     const int first = (int)blockIdx.x * per;
     const int nmine = min(per, ntile - first);
-    if (nmine <= 0) return 0.0;
+    if (nmine <= 0) return;
     const unsigned base = sm.seq;
     if (tid == 0)
         for (int k = 0; k < NSTAGE && k < nmine; ++k) {
-            const int t0 = (first + k) * UT;
-            update_issue(P, sm, (base + k) % NSTAGE, t0, min(UT, m - t0));
+            const int t0 = (first + k) * TS;
+            tile_issue<NV>(io, sm, (base + k) % NSTAGE, t0, min(TS, len - t0));
         }
     for (int j = 0; j < nmine; ++j) {
         const unsigned u = base + j;
         const int s = u % NSTAGE;
-        const int t0 = (first + j) * UT;
-        const int cnt = min(UT, m - t0);
+        const int t0 = (first + j) * TS;
+        const int cnt = min(TS, len - t0);
         double *buf = reinterpret_cast<double *>(&sm.st[s]);
         mbar_wait(&sm.full[s], (u / NSTAGE) & 1u, S.abort_flag);
-        for (int e = tid; e < cnt; e += THREADS) {
-            const double ri = buf[e], wi = buf[UT + e];
-            const double pi = ri + beta * buf[2 * UT + e];
-            const double si = wi + beta * buf[3 * UT + e];
-            const double vi = buf[4 * UT + e] + alpha * pi;
-            const double rn = ri - alpha * si;
-            buf[2 * UT + e] = pi; buf[3 * UT + e] = si; buf[4 * UT + e] = vi; buf[e] = rn;
-            gpart += rn * rn;
-        }
+        for (int e = tid; e < cnt; e += THREADS) f(buf, e);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
@@ -887,22 +892,22 @@ __device__ __noinline__ double cg_update(const ProjView &P, Smem &sm, const Sync
             // peer has just pushed): an odd last entry goes out by plain stores
             const unsigned bytes = (unsigned)((cnt & ~1) * 8);
             if (bytes) {
-                bulk_s2g(P.r + t0, buf, bytes);
-                bulk_s2g(P.p + t0, buf + 2 * UT, bytes);
-                bulk_s2g(P.s + t0, buf + 3 * UT, bytes);
-                bulk_s2g(P.v + t0, buf + 4 * UT, bytes);
+#pragma unroll
+                for (int k = 0; k < NV; ++k)
+                    if (io.out[k]) bulk_s2g(io.out[k] + t0, buf + k * TS, bytes);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             if (cnt & 1) {
                 const int e = cnt - 1;
-                P.r[t0 + e] = buf[e]; P.p[t0 + e] = buf[2 * UT + e];
-                P.s[t0 + e] = buf[3 * UT + e]; P.v[t0 + e] = buf[4 * UT + e];
+#pragma unroll
+                for (int k = 0; k < NV; ++k)
+                    if (io.out[k]) io.out[k][t0 + e] = buf[k * TS + e];
             }
             if (j + NSTAGE < nmine) {
                 // the stores must have read the stage before it is refilled
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                const int n0 = (first + j + NSTAGE) * UT;
-                update_issue(P, sm, s, n0, min(UT, m - n0));
+                const int n0 = (first + j + NSTAGE) * TS;
+                tile_issue<NV>(io, sm, s, n0, min(TS, len - n0));
             }
         }
     }
@@ -912,142 +917,232 @@ __device__ __noinline__ double cg_update(const ProjView &P, Smem &sm, const Sync
         sm.seq = base + (unsigned)nmine;
     }
     __syncthreads();
+}
+
+// ---------------------------------------------------------------- fused CG update
+// p = r + beta p;  s = w + beta s;  v += alpha p;  r -= alpha s;  returns this
+// thread's share of r.r -- the one vector pass of the inner CG iteration
+// (5 reads + 4 writes of m-vectors).
+__device__ __noinline__ double cg_update(const ProjView &P, Smem &sm, const SyncView &S,
+                                         double alpha, double beta) {
+    constexpr int TS = (int)((sizeof(Stage) / (5 * sizeof(double))) & ~(size_t)31);
+    TileIO<5> io = {{P.r, P.w, P.p, P.s, P.v}, {P.r, nullptr, P.p, P.s, P.v}};
+    double gpart = 0.0;
+    tile_pass<5>(sm, S, P.m, io, [&](double *t, int e) {
+        const double ri = t[e], wi = t[TS + e];
+        const double pi = ri + beta * t[2 * TS + e];
+        const double si = wi + beta * t[3 * TS + e];
+        const double vi = t[4 * TS + e] + alpha * pi;
+        const double rn = ri - alpha * si;
+        t[2 * TS + e] = pi; t[3 * TS + e] = si; t[4 * TS + e] = vi; t[e] = rn;
+        gpart += rn * rn;
+    });
     return gpart;
 }
 
 // ---------------------------------------------------------------- banded sweep
 // 4 consecutive entries of a vector (row % 4 == 0, vectors are 256-byte
 // aligned); rows outside [0, m) read as 0.
-__device__ __forceinline__ void ld4_guard(const double *v, long long row, int m, double out[4]) {
-    if (row >= 0 && row + 3 < m) {
+__device__ __forceinline__ void ld4_guard(const double *v, int row, int lo, int hi, double out[4]) {
+    if (row >= lo && row + 3 < hi) {
         const double2 a = *reinterpret_cast<const double2 *>(v + row);
         const double2 b = *reinterpret_cast<const double2 *>(v + row + 2);
         out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
     } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const long long r = row + q;
-            out[q] = (r >= 0 && r < m) ? v[r] : 0.0;
+            const int r = row + q;
+            out[q] = (r >= lo && r < hi) ? v[r] : 0.0;
         }
     }
 }
 
-// lane 0 of a warp: start the bulk copy of one sweep step (32 chunks x HB
-// doubles, 2 KB contiguous) into ring buffer ``u % BAND_NBUF`` of the warp.
-__device__ __forceinline__ void band_issue(double *ring, unsigned long long *bar, unsigned u,
-                                           const double *src) {
-    const unsigned b = u % BAND_NBUF;
+// ---- per-warp ring of sweep steps.  One step = the factor rows of the warp's
+// 32 chunks, [HB][32] doubles = 2 KB contiguous in HBM, landed by one TMA bulk
+// copy on the buffer's mbarrier.  All addresses are 32-bit shared-window
+// addresses kept incrementally: the step loop is instruction-bound when few
+// warps per SM are active, so its bookkeeping is pared down to a few
+// integer instructions.
+struct BandRing {
+    unsigned data;      // shared address of buffer 0, this lane's column (+ lane * 8)
+    unsigned bars;      // shared address of the mbarrier of buffer 0
+    unsigned mask;      // NB - 1
+    unsigned b, par;    // buffer and phase parity of the next step to consume
+};
+
+__device__ __forceinline__ void ring_issue(const BandRing &R, unsigned buf, const double *src) {
+    // The buffer was last READ through the generic proxy by the lanes of this
+    // warp and the __syncwarp() before this call orders those reads before the
+    // copy (consumer release / producer acquire of a TMA pipeline; a proxy
+    // fence is for generic WRITES the async proxy must see and would cost
+    // hundreds of cycles per step here).
     constexpr unsigned BYTES = HB * 32 * sizeof(double);
-    // the buffer was last read through the generic proxy (shared memory only:
-    // an unqualified proxy fence would also wait for this thread's global
-    // loads in flight and serialise the steps on the HBM latency)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                 ::"r"(smem_addr(&bar[b])), "r"(BYTES) : "memory");
-    bulk_g2s(ring + b * (HB * 32), src, BYTES, &bar[b]);
+    const unsigned bar = R.bars + buf * 8u;
+    const unsigned dst = R.data + buf * BYTES;          // lane 0 only: its column is the buffer start
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BYTES) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(BYTES), "r"(bar) : "memory");
+}
+
+template <int OFF>
+__device__ __forceinline__ double lds_off(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+struct BandRow { double l0, l1, l2, l3, l4, l5, l6, l7; };
+
+// wait for the next step of the ring, read this lane's factor row, advance
+__device__ __forceinline__ BandRow ring_next(BandRing &R, int *abort_flag) {
+    const unsigned bar = R.bars + R.b * 8u;
+    unsigned spins = 0, done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(bar), "r"(R.par) : "memory");
+        if (!done && ++spins > (1u << 24)) { *abort_flag = 6; __trap(); }
+    } while (!done);
+    const unsigned a = R.data + R.b * (unsigned)(HB * 32 * sizeof(double));
+    BandRow r;
+    r.l0 = lds_off<0>(a);    r.l1 = lds_off<256>(a);  r.l2 = lds_off<512>(a);  r.l3 = lds_off<768>(a);
+    r.l4 = lds_off<1024>(a); r.l5 = lds_off<1280>(a); r.l6 = lds_off<1536>(a); r.l7 = lds_off<1792>(a);
+    R.b = (R.b + 1u) & R.mask;
+    R.par ^= (R.b == 0u);
+    return r;
 }
 
 // out (+)= L^-T L^-1 in, chunk by chunk (see BandView).  Thread = chunk: a
 // forward substitution over the chunk's B + 2 ov rows from a zero start, the
 // result of rows >= ov kept in Bd.y, then the backward substitution down to
 // the first owned row; only the B owned rows are written.  The factor rows of
-// the warp's 32 chunks arrive step by step through a 4-deep ring of TMA bulk
-// copies, so no registers hold loads in flight and the 2 KB blocks are read
-// from HBM fully coalesced.  Returns this thread's share of ||in||^2 (owned
-// rows).  ``in`` and ``out`` must not alias.
+// the warp's 32 chunks arrive step by step through a ring of TMA bulk copies
+// (4 to 16 deep), so no registers hold loads in flight and the 2 KB blocks are
+// read from HBM fully coalesced; the recurrences are arranged so that only one
+// multiply-add and one multiply lie between consecutive steps.
+// Returns this thread's share of ||in||^2 (owned rows).  ``in`` and ``out``
+// must not alias.
 __device__ __noinline__ double band_sweep(const ProjView &P, const SyncView &S, Smem &sm,
                                           const double *in, double *out, int accumulate) {
     const BandView &Bd = P.band;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = P.m, B = Bd.B, ov = Bd.ov, steps = Bd.steps;
-    double *ring = reinterpret_cast<double *>(&sm.st[0]) + (size_t)warp * (BAND_NBUF * HB * 32);
-    unsigned long long *bar = sm.bfull[warp];
+    // ring depth: the WARPS * 4 step buffers (64 KB of the stages) are shared by
+    // the warps of the CTA that have a group at all -- few groups per CTA (large
+    // chunks, or a small / row-partitioned problem) get deep rings, so the bulk
+    // copies in flight still cover the HBM latency
+    const int wact = max(1, min(WARPS, (Bd.ngroup + (int)gridDim.x - 1) / (int)gridDim.x));
+    const int NB = wact <= 2 ? 16 : (wact <= 4 ? 8 : 4);
+    constexpr int STEP = HB * 32;          // doubles per step
+    const int in_lo = Bd.in_lo, in_hi = Bd.in_hi;
     double ss = 0.0;
+    // row-partitioned: the neighbours' rows next to the own block are ghosts of
+    // ``in``; only the first and the last group read them and wait for them
+    const bool dist = S.C.size > 1;
+    if (dist) halo_sync(S, sm, in, 1);
     __syncthreads();                       // the stages are free (previous phase of this CTA is over)
-    unsigned useq = sm.bseq[warp];
+    BandRing R;
+    R.data = smem_addr(reinterpret_cast<double *>(&sm.st[0]) + (size_t)warp * (NB * STEP)) + lane * 8u;
+    R.bars = smem_addr(sm.bfull + warp * NB);
+    R.mask = (unsigned)NB - 1u;
+    {
+        const unsigned useq = sm.bseq[warp];
+        R.b = useq & R.mask;
+        R.par = (useq / (unsigned)NB) & 1u;
+    }
+    unsigned used = 0;
     for (int g = (int)blockIdx.x + (int)gridDim.x * warp; g < Bd.ngroup; g += (int)gridDim.x * WARPS) {
-        const double *Lg = Bd.L + (size_t)g * steps * (HB * 32);
-        const long long e0 = ((long long)g * 32 + lane) * B - ov;      // row of step 0
-        double *yg = Bd.y + (size_t)g * (B + ov) * 32 + lane;
+        const double *Lg = Bd.L + (size_t)g * steps * STEP;
+        const int e0 = (g * 32 + lane) * B - ov;                       // row of step 0
+        double *yp = Bd.y + (size_t)g * (B + ov) * 32 + lane;          // forward result of row e0 + ov
+        if (dist && (g == 0 || g == Bd.ngroup - 1)) ghost_wait(S, sm, 1);
         // ================= forward: steps 0 .. steps-1
         {
             __syncwarp();
+            const double *src = Lg;
+            int left = steps;                                          // steps not yet requested
             if (lane == 0)
-                for (int q = 0; q < BAND_NBUF - 1 && q < steps; ++q)
-                    band_issue(ring, bar, useq + q, Lg + (size_t)q * (HB * 32));
+                for (int q = 0; q < NB && left > 0; ++q, --left, src += STEP)
+                    ring_issue(R, (R.b + q) & R.mask, src);
+            left = max(0, steps - NB); src = Lg + (size_t)min(steps, NB) * STEP;
             double y1 = 0, y2 = 0, y3 = 0, y4 = 0, y5 = 0, y6 = 0, y7 = 0;
             double rn[4];
-            ld4_guard(in, e0, m, rn);
+            ld4_guard(in, e0, in_lo, in_hi, rn);
+            unsigned freed = 0;
             for (int jb = 0; jb < steps; jb += 4) {
                 const double rc[4] = {rn[0], rn[1], rn[2], rn[3]};
-                if (jb + 4 < steps) ld4_guard(in, e0 + jb + 4, m, rn);
+                if (jb + 4 < steps) ld4_guard(in, e0 + jb + 4, in_lo, in_hi, rn);
+                const bool keep = jb >= ov, own = keep && jb < ov + B;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int j = jb + q;
-                    const unsigned u = useq + (unsigned)j;
-                    __syncwarp();           // every lane is done with the buffer of step j-1
-                    if (lane == 0 && j + BAND_NBUF - 1 < steps)
-                        band_issue(ring, bar, u + BAND_NBUF - 1, Lg + (size_t)(j + BAND_NBUF - 1) * (HB * 32));
-                    mbar_wait(&bar[u % BAND_NBUF], (u / BAND_NBUF) & 1u, S.abort_flag);
-                    const double *Lr = ring + (u % BAND_NBUF) * (HB * 32) + lane;
-                    double t = rc[q];
-                    t = __fma_rn(-Lr[7 * 32], y7, t);
-                    t = __fma_rn(-Lr[6 * 32], y6, t);
-                    t = __fma_rn(-Lr[5 * 32], y5, t);
-                    t = __fma_rn(-Lr[4 * 32], y4, t);
-                    t = __fma_rn(-Lr[3 * 32], y3, t);
-                    t = __fma_rn(-Lr[2 * 32], y2, t);
-                    t = __fma_rn(-Lr[1 * 32], y1, t);
-                    const double y = t * Lr[0];
-                    y7 = y6; y6 = y5; y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;
-                    if (j >= ov) {
-                        yg[(size_t)(j - ov) * 32] = y;
-                        if (j < ov + B) ss += rc[q] * rc[q];
+                    __syncwarp();           // every lane has read the row of the previous step
+                    if (lane == 0 && (jb | q) != 0 && left > 0) {
+                        ring_issue(R, freed, src);
+                        src += STEP; --left;
                     }
+                    freed = R.b;
+                    const BandRow L = ring_next(R, S.abort_flag);
+                    // y_j = (r_j - sum_k L[j][j-k] y_{j-k}) / L_jj; y_{j-1} enters last
+                    const double pa = __fma_rn(L.l7, y7, __fma_rn(L.l5, y5, L.l3 * y3));
+                    const double pb = __fma_rn(L.l6, y6, __fma_rn(L.l4, y4, L.l2 * y2));
+                    const double t = __fma_rn(-L.l1, y1, rc[q] - (pa + pb));
+                    const double y = t * L.l0;
+                    y7 = y6; y6 = y5; y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;
+                    if (keep) { *yp = y; yp += 32; }
+                    if (own) ss += rc[q] * rc[q];
                 }
             }
-            useq += (unsigned)steps;
+            used += (unsigned)steps;
         }
         // ================= backward: steps steps-1 .. ov
         {
             const int nst = steps - ov;
             __syncwarp();
+            const double *src = Lg + (size_t)(steps - 1) * STEP;
+            int left = nst;
             if (lane == 0)
-                for (int q = 0; q < BAND_NBUF - 1 && q < nst; ++q)
-                    band_issue(ring, bar, useq + q, Lg + (size_t)(steps - 1 - q) * (HB * 32));
+                for (int q = 0; q < NB && left > 0; ++q, --left, src -= STEP)
+                    ring_issue(R, (R.b + q) & R.mask, src);
+            left = max(0, nst - NB); src = Lg + (size_t)(steps - 1 - min(nst, NB)) * STEP;
+            // c_k: what the rows above contribute to row j-k (k = 0: this row)
             double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
             double yn[4];
+            yp -= 4 * 32;                   // forward result of the 4 rows of the first block
 #pragma unroll
-            for (int q = 0; q < 4; ++q) yn[q] = yg[(size_t)(steps - 4 + q - ov) * 32];
+            for (int q = 0; q < 4; ++q) yn[q] = yp[q * 32];
+            unsigned freed = 0;
             for (int jb = steps - 4; jb >= ov; jb -= 4) {
                 const double yc[4] = {yn[0], yn[1], yn[2], yn[3]};
                 if (jb - 4 >= ov) {
+                    yp -= 4 * 32;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) yn[q] = yg[(size_t)(jb - 4 + q - ov) * 32];
+                    for (int q = 0; q < 4; ++q) yn[q] = yp[q * 32];
                 }
                 double zo[4];
 #pragma unroll
                 for (int q = 3; q >= 0; --q) {
-                    const int j = jb + q;
-                    const int sidx = steps - 1 - j;
-                    const unsigned u = useq + (unsigned)sidx;
                     __syncwarp();
-                    if (lane == 0 && sidx + BAND_NBUF - 1 < nst)
-                        band_issue(ring, bar, u + BAND_NBUF - 1, Lg + (size_t)(j - (BAND_NBUF - 1)) * (HB * 32));
-                    mbar_wait(&bar[u % BAND_NBUF], (u / BAND_NBUF) & 1u, S.abort_flag);
-                    const double *Lr = ring + (u % BAND_NBUF) * (HB * 32) + lane;
-                    const double z = (yc[q] - c0) * Lr[0];
-                    c0 = __fma_rn(Lr[1 * 32], z, c1);
-                    c1 = __fma_rn(Lr[2 * 32], z, c2);
-                    c2 = __fma_rn(Lr[3 * 32], z, c3);
-                    c3 = __fma_rn(Lr[4 * 32], z, c4);
-                    c4 = __fma_rn(Lr[5 * 32], z, c5);
-                    c5 = __fma_rn(Lr[6 * 32], z, c6);
-                    c6 = Lr[7 * 32] * z;
+                    if (lane == 0 && (jb != steps - 4 || q != 3) && left > 0) {
+                        ring_issue(R, freed, src);
+                        src -= STEP; --left;
+                    }
+                    freed = R.b;
+                    const BandRow L = ring_next(R, S.abort_flag);
+                    const double z = (yc[q] - c0) * L.l0;
+                    c0 = __fma_rn(L.l1, z, c1);
+                    c1 = __fma_rn(L.l2, z, c2);
+                    c2 = __fma_rn(L.l3, z, c3);
+                    c3 = __fma_rn(L.l4, z, c4);
+                    c4 = __fma_rn(L.l5, z, c5);
+                    c5 = __fma_rn(L.l6, z, c6);
+                    c6 = L.l7 * z;
                     zo[q] = z;
                 }
                 if (jb < ov + B) {
-                    const long long row = e0 + jb;       // >= 0: an owned row
+                    const int row = e0 + jb;             // >= 0: an owned row
                     if (row + 3 < m) {
                         double2 a = make_double2(zo[0], zo[1]), b = make_double2(zo[2], zo[3]);
                         if (accumulate) {
@@ -1064,11 +1159,11 @@ __device__ __noinline__ double band_sweep(const ProjView &P, const SyncView &S, 
                     }
                 }
             }
-            useq += (unsigned)nst;
+            used += (unsigned)nst;
         }
     }
     __syncwarp();
-    if (lane == 0) sm.bseq[warp] = useq;
+    if (lane == 0) sm.bseq[warp] += used;
     __syncthreads();
     return ss;
 }
@@ -1652,13 +1747,26 @@ k_projected_cg(const PcgArgs a) {
             // x_next = x + alpha p; ||x_next||^2; inside-box flag;
             // r_next = r + alpha H_p (:622) in the same pass.
             double sq = 0.0, out = 0.0;
-            for (int i = gt; i < n; i += nt) {
-                double pi = p[i];
-                double v = x[i] + alpha * pi;
-                xn[i] = v;
-                sq += v * v;
-                if (a.has_box && (v < a.lb[i] || v > a.ub[i])) out = 1.0;
-                a.tmp[i] = r[i] + alpha * Hp[i];
+            if (!a.has_box) {
+                constexpr int TS = (int)((sizeof(Stage) / (4 * sizeof(double))) & ~(size_t)31);
+                TileIO<4> io = {{x, p, r, Hp}, {xn, nullptr, a.tmp, nullptr}};
+                tile_pass<4>(sm, S, n, io, [&](double *t, int e) {
+                    const double v = t[e] + alpha * t[TS + e];
+                    t[e] = v;
+                    sq += v * v;
+                    t[2 * TS + e] = t[2 * TS + e] + alpha * t[3 * TS + e];
+                });
+            } else {
+                constexpr int TS = (int)((sizeof(Stage) / (6 * sizeof(double))) & ~(size_t)31);
+                TileIO<6> io = {{x, p, r, Hp, a.lb, a.ub},
+                                {xn, nullptr, a.tmp, nullptr, nullptr, nullptr}};
+                tile_pass<6>(sm, S, n, io, [&](double *t, int e) {
+                    const double v = t[e] + alpha * t[TS + e];
+                    t[e] = v;
+                    sq += v * v;
+                    if (v < t[4 * TS + e] || v > t[5 * TS + e]) out = 1.0;
+                    t[2 * TS + e] = t[2 * TS + e] + alpha * t[3 * TS + e];
+                });
             }
             publish(S, sm, 0, sq, OP_SUM);
             publish(S, sm, 1, out, OP_MAX);
@@ -1698,7 +1806,13 @@ k_projected_cg(const PcgArgs a) {
             double ng2 = sqrt(gg2);
             double rt_g_next = ng2 * ng2;                            // :626
             double beta = rt_g_next / rt_g;                          // :627
-            for (int i = gt; i < n; i += nt) p[i] = -r[i] + beta * p[i];   // :628
+            {                                                        // p = -g_next + beta p  (:628)
+                constexpr int TS = (int)((sizeof(Stage) / (2 * sizeof(double))) & ~(size_t)31);
+                TileIO<2> io = {{r, p}, {nullptr, p}};
+                tile_pass<2>(sm, S, n, io, [&](double *t, int e) {
+                    t[TS + e] = -t[e] + beta * t[TS + e];
+                });
+            }
             { double *t = x; x = xn; xn = t; x_slot ^= 1; }          // :630
             rt_g = rt_g_next;                                        // :633
             grid_sync(S, sm);
@@ -2173,7 +2287,7 @@ __global__ void k_band_factor(int m, const int *rowptr, const int *col, const do
 // Lint[g][j][k][lane] = Lrow[(g*32+lane)*B - ov + j][k]; rows outside the
 // matrix are identity rows (1/L_ii = 1, no couplings).
 __global__ void k_band_interleave(int m, int B, int ov, int steps, long long total,
-                                  const double *Lrow, double *Lint) {
+                                  long long row_off, const double *Lrow, double *Lint) {
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int lane = (int)(idx & 31);
@@ -2181,7 +2295,9 @@ __global__ void k_band_interleave(int m, int B, int ov, int steps, long long tot
     const long long gj = idx >> 8;                  // g * steps + j
     const long long g = gj / steps;
     const int j = (int)(gj - g * steps);
-    const long long i = (g * 32 + lane) * B - ov + j;
+    // row_off: index of the own row 0 within the factored rows (a row-partitioned
+    // rank factors its own rows plus a margin of its neighbours')
+    const long long i = (g * 32 + lane) * B - ov + j + row_off;
     Lint[idx] = (i >= 0 && i < m) ? Lrow[i * HB + k] : (k == 0 ? 1.0 : 0.0);
 }
 

@@ -104,6 +104,7 @@ PROTOTYPES = {
     "ipb_csr_set_space": (C.c_int, [_P, _P, C.c_int]),
     "ipb_proj_create_parts": (C.c_int, [_P, _P, _P, _P, _P, _P, _D, C.c_double, C.c_double,
                                         C.c_int, C.c_double, C.c_int, C.POINTER(_P)]),
+    "ipb_proj_set_band_parts": (C.c_int, [_P, _P, _P, _I64, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ipb_vec_create": (C.c_int, [_P, _I64, C.POINTER(_P)]),
     "ipb_vec_destroy": (C.c_int, [_P, _P]),
     "ipb_vec_upload": (C.c_int, [_P, _P, _D]),
@@ -112,6 +113,8 @@ PROTOTYPES = {
     "ipb_vec_ptr": (_P, [_P]),
     "ipb_host_alloc": (C.c_int, [_P, _I64, C.POINTER(_P)]),
     "ipb_host_free": (C.c_int, [_P, _P]),
+    "ipb_trace_enable": (C.c_int, [_P, C.c_int]),
+    "ipb_trace_read": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]),
     "ipb_timer_start": (C.c_int, [_P]),
     "ipb_timer_stop": (C.c_int, [_P, _D]),
     "ipb_bench_inner_iterations": (C.c_int, [_P, _P, _P, C.c_int, _D]),

@@ -93,6 +93,21 @@ class Context:
     def sync(self):
         self.check(self.lib.ipb_ctx_sync(self.h))
 
+    def trace(self, capacity):
+        """Record the time of every grid barrier of the following launches
+        (0: off); read with :meth:`trace_read`."""
+        self._trace_cap = int(capacity)
+        self.check(self.lib.ipb_trace_enable(self.h, int(capacity)))
+
+    def trace_read(self):
+        """Barrier times (ns, numpy uint64) of the last launch."""
+        cap = getattr(self, "_trace_cap", 0)
+        buf = np.zeros(max(cap, 1), dtype=np.uint64)
+        cnt = C.c_int()
+        self.check(self.lib.ipb_trace_read(
+            self.h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), cap, C.byref(cnt)))
+        return buf[:min(cnt.value, cap)]
+
     def timer_start(self):
         self.check(self.lib.ipb_timer_start(self.h))
 

@@ -24,6 +24,11 @@ import numpy as np
 import scipy.sparse as sps
 
 N_SPACE, M_SPACE = 0, 1
+# banded direct solve of (A A')^-1 (csrc/device.cuh, BandView): rows of the
+# neighbours a rank's sweeps read next to its own block, and the extra margin
+# of rows of M it factorises so that the truncated factor recurrence has
+# forgotten its start where it is used
+BAND_HALO, BAND_MARGIN = 48, 96
 
 
 class RowPartition:
@@ -77,15 +82,39 @@ def _localize(M, lo, hi, ghosts_lo, ghosts_hi):
     return L
 
 
+def band_window(part, rank):
+    """Rows of M = A~ A~' a rank factorises for the banded direct solve:
+    ``(e0, e1, ghost_below, ghost_above)`` -- own rows plus BAND_MARGIN on each
+    side (clipped to the matrix), and how many rows of each neighbour the
+    sweeps read."""
+    m0, m1 = part.own(rank, M_SPACE)
+    return (max(0, m0 - BAND_MARGIN), min(part.m, m1 + BAND_MARGIN),
+            min(BAND_HALO, m0), min(BAND_HALO, part.m - m1))
+
+
 def _assemble(part, rank, H_rows, A_rows, An_rows, At_rows, Ant_rows, M_rows, dscale_own,
-              fro2_own):
+              fro2_own, M_ext=None):
     """Local column numbering + ghost lists from this rank's row blocks (all
-    with GLOBAL column indices)."""
+    with GLOBAL column indices).  ``M_ext``: rows and columns
+    ``band_window(part, rank)[:2]`` of M in the window's own numbering (or
+    None: no banded solve); the m-space ghost zones then also hold the sweeps'
+    halo rows."""
     n0, n1 = part.own(rank, N_SPACE)
     m0, m1 = part.own(rank, M_SPACE)
     # ghost entries per space: union over the matrices whose columns live there
     gn = np.union1d(_remote_columns(H_rows, n0, n1), _remote_columns(A_rows, n0, n1))
     gm = np.union1d(_remote_columns(At_rows, m0, m1), _remote_columns(M_rows, m0, m1))
+    band = None
+    if M_ext is not None and m1 > m0:
+        e0, e1, gb, ga = band_window(part, rank)
+        halo = np.concatenate((np.arange(m0 - gb, m0), np.arange(m1, m1 + ga)))
+        gm_band = np.union1d(gm, halo)
+        lo_ok = np.array_equal(gm_band[gm_band < m0], np.arange(m0 - gb, m0))
+        hi_ok = np.array_equal(gm_band[gm_band >= m1], np.arange(m1, m1 + ga))
+        if lo_ok and hi_ok:        # the sweeps address ghost rows by offset: zones must be contiguous
+            gm = gm_band
+            band = {"M_ext": sps.csr_matrix(M_ext), "ext_off": m0 - e0, "ghost_below": gb,
+                    "ghost_above": ga}
     ghosts = {N_SPACE: (gn[gn < n0], gn[gn >= n1]), M_SPACE: (gm[gm < m0], gm[gm >= m1])}
     loc_n = lambda X: _localize(X, n0, n1, *ghosts[N_SPACE])      # noqa: E731
     loc_m = lambda X: _localize(X, m0, m1, *ghosts[M_SPACE])      # noqa: E731
@@ -93,7 +122,7 @@ def _assemble(part, rank, H_rows, A_rows, An_rows, At_rows, Ant_rows, M_rows, ds
         "H": loc_n(H_rows), "A_raw": loc_n(A_rows), "A_norm": loc_n(An_rows),
         "At_raw": loc_m(At_rows), "At_norm": loc_m(Ant_rows), "M": loc_m(M_rows),
         "ghosts": ghosts, "dscale": np.ascontiguousarray(dscale_own), "fro2_own": float(fro2_own),
-        "own": {N_SPACE: (n0, n1), M_SPACE: (m0, m1)},
+        "own": {N_SPACE: (n0, n1), M_SPACE: (m0, m1)}, "band": band,
     }
 
 
@@ -126,13 +155,16 @@ def local_parts(part, rank, H, A):
     Ant.sort_indices()
     M_rows = sps.csr_matrix(An[m0:m1] @ An.T)        # own rows of A~ A~'
     M_rows.sort_indices()
+    e0, e1 = band_window(part, rank)[:2]
+    M_ext = sps.csr_matrix(An[e0:e1] @ An[e0:e1].T)  # window of M for the banded factor
+    M_ext.sort_indices()
     out = _assemble(part, rank, H[n0:n1], A[m0:m1], An[m0:m1], At[n0:n1], Ant[n0:n1], M_rows,
-                    dscale[m0:m1], row_norm2[m0:m1].sum())
+                    dscale[m0:m1], row_norm2[m0:m1].sum(), M_ext)
     out["fro"] = float(np.sqrt(row_norm2.sum()))
     return out
 
 
-def local_parts_generated(part, rank, kappa=1e4, seed=0, margin=16):
+def local_parts_generated(part, rank, kappa=1e4, seed=0, margin=BAND_MARGIN + 16):
     """The same pieces for the index-addressable synthetic QP
     (``synthetic.hashed_*``), built from a WINDOW of rows around the rank's own
     block: no rank ever holds the whole problem (BASELINE config 5).  The
@@ -163,6 +195,10 @@ def local_parts_generated(part, rank, kappa=1e4, seed=0, margin=16):
     r0, r1 = m0 - w0, m1 - w0                                         # own rows in the window
     Mw = sps.csr_matrix(Anw[r0:r1] @ Anw.T)
     Mw.sort_indices()
+    e0, e1 = band_window(part, rank)[:2]
+    assert w0 <= e0 and e1 <= w1, "window does not cover the banded factor's margin"
+    M_ext = sps.csr_matrix(Anw[e0 - w0:e1 - w0] @ Anw[e0 - w0:e1 - w0].T)
+    M_ext.sort_indices()
 
     def to_global(X, col_off, ncols):
         X = sps.csr_matrix(X)
@@ -179,7 +215,7 @@ def local_parts_generated(part, rank, kappa=1e4, seed=0, margin=16):
     return _assemble(part, rank, H_rows, to_global(Aw[r0:r1], c_lo, n),
                      to_global(Anw[r0:r1], c_lo, n), to_global(At_rows, w0, m),
                      to_global(Ant_rows, w0, m), to_global(Mw, w0, m), dscale[r0:r1],
-                     row_norm2[r0:r1].sum())
+                     row_norm2[r0:r1].sum(), M_ext)
 
 
 def send_lists(part, rank, all_ghosts, glo_cap=None):
@@ -253,7 +289,7 @@ class DistSolver:
 
     def __init__(self, H, A, rank, size, group=None, device=None, inner_rtol=1e-13,
                  inner_maxit=1000, orth_tol=1e-12, max_refin=3, explicit_aat=True,
-                 generated=None):
+                 generated=None, band=True, band_chunk_rows=0):
         """``H``, ``A``: the global matrices (every rank holds them), or None with
         ``generated=dict(n=..., kappa=..., seed=...)``: the index-addressable
         synthetic QP, each rank generating only a window around its own rows."""
@@ -314,6 +350,25 @@ class DistSolver:
             parts["fro"], float(orth_tol), int(max_refin), float(inner_rtol), int(inner_maxit),
             C.byref(ph)))
         self.proj = _ProjHandle(ctx, ph, self.m_own, self.n_own)
+        # banded direct solve: every rank must take the same decision (the sweeps
+        # exchange halos), so it is used only if every rank can
+        can = bool(band and explicit_aat and parts["band"] is not None)
+        votes = [None] * size
+        dist.all_gather_object(votes, can or self.m_own == 0, group=group)
+        self.band = False
+        if all(votes) and self.m_own > 0:
+            bd = parts["band"]
+            self.M_ext = dev.DeviceCSR(ctx, bd["M_ext"], with_transpose=False)
+            ctx.check(lib.ipb_proj_set_band_parts(
+                ctx.h, ph, self.M_ext.h, int(bd["ext_off"]), int(bd["ghost_below"]),
+                int(bd["ghost_above"]), int(band_chunk_rows), BAND_HALO))
+            info = (C.c_int32 * 6)()
+            ctx.check(lib.ipb_proj_band_info(ctx.h, ph, info))
+            self.band = bool(info[0])
+        used = [None] * size
+        dist.all_gather_object(used, self.band, group=group)
+        if len(set(used)) != 1:
+            raise RuntimeError("ranks disagree on the banded solve: %s" % used)
         dist.barrier(group=group)
         self.group = group
 

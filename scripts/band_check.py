@@ -65,3 +65,13 @@ xc = dx.download()
 print("CG-only projected_cg: kernel %.3f ms inner %d; x rel diff band vs CG %.2e" % (
     info.kernel_ms, info.inner_iters, np.linalg.norm(xb - xc) / np.linalg.norm(xc)))
 print(json.dumps(out))
+# ---- phase timeline of one 8-iteration launch (banded path, default chunk size)
+proj.set_band(0, int(sys.argv[3]) if len(sys.argv) > 3 else 0, 0)
+device.projected_cg_dev(proj, Hd, dc, db, dx, tol=1e-30, max_iter=8)
+ctx.trace(4000)
+info = device.projected_cg_dev(proj, Hd, dc, db, dx, tol=1e-30, max_iter=8)
+t = ctx.trace_read().astype(np.int64)
+ctx.trace(0)
+d = np.diff(t) / 1e3
+print("timeline: %d barriers, kernel %.3f ms, sum of phases %.3f ms" % (len(t), info.kernel_ms, d.sum() / 1e3))
+print("phases (us):", " ".join("%.0f" % v for v in d))
