@@ -43,38 +43,56 @@ METRIC = "projected_cg_iterations_per_s"
 UNIT = "it/s"
 
 
-def algorithmic_bytes(n, m, nnzH, nnzA, nnzM, niter, inner_iters, n_z, n_refin, n_hp):
+def algorithmic_bytes(n, m, nnzH, nnzA, nnzM, niter, inner_iters, n_solves, n_refin, n_hp,
+                     n_sweeps=0, has_b=1):
     """Compulsory HBM bytes of one launch of the solve kernel, for the
     algorithm AS RUN.  8-byte values, 4-byte indices,
     every matrix / vector counted once per logical read or write:
 
       B_spmv(rows, cols, nnz) = 12 nnz + 4 (rows+1) + 8 cols + 8 rows
-      inner CG iteration, explicit M = A A' (nnzM > 0):
-          B_in = B_spmv(m, m, nnzM) + 72 m     (one SpMV; fused update = 5 reads + 4 writes)
-      inner CG iteration, A then A' (nnzM < 0):
-          B_in = B_A + B_At + 8 m + 72 m       (two SpMVs, re-read of r for the dot)
-      one Z apply = 2 B_A + B_At + 16 n (+ its inner iterations), again per refinement
-          (A x, A' v with the re-read of x, the orthogonality product A z, ||x||^2)
-      outer iteration = B_H + 72 n (+ its Z apply)
+      outer iteration = B_H + 72 n  (+ its Z apply)
+      Z apply = 2 B_A + B_At + 8 n  (A~ x, z = x - A~' v with the re-read of x,
+                the orthogonality product A z)  + its (A A')^-1 solve
+      (A A')^-1 by the banded direct solve (n_sweeps > 0):
+          B_sweep = 160 m per sweep: the factor rows once forwards and once
+          backwards (2 x 64 m), right-hand side (8 m), forward result written
+          and read back (16 m), solution (8 m).  Rows read again in the overlap
+          of neighbouring chunks are NOT counted (they are waste, visible as
+          ncu traffic above this figure).  Z applies are verified by the
+          orthogonality product they contain; the Y / LS solves by one product
+          with M (B_M + 8 m).
+      (A A')^-1 by CG (n_sweeps == 0), per inner iteration:
+          explicit M = A A' (nnzM > 0):  B_in = B_spmv(m, m, nnzM) + 72 m
+          A then A' (nnzM < 0):          B_in = B_A + B_At + 8 m + 72 m
 
     ``survey`` is the same launch priced with SURVEY.md section 8d's model
-    (B_in = B_A + B_At + 56 m: two SpMVs and an idealised 7-pass update),
-    i.e. the traffic the reference formulation would need."""
+    of the reference formulation (an inner CG of k_in = 35 iterations per
+    solve, B_in = B_A + B_At + 56 m), i.e. the traffic the path would need
+    without the direct solve."""
     B_H = 12 * nnzH + 4 * (n + 1) + 16 * n
     B_A = 12 * nnzA + 4 * (m + 1) + 8 * n + 8 * m
     B_At = 12 * nnzA + 4 * (n + 1) + 8 * m + 8 * n
-    if nnzM > 0:
-        B_M = 12 * nnzM + 4 * (m + 1) + 16 * m
-        B_in = B_M + 72 * m
-    else:
-        B_M = None
-        B_in = B_A + B_At + 8 * m + 72 * m
+    B_M = 12 * nnzM + 4 * (m + 1) + 16 * m if nnzM > 0 else None
     B_in_survey = B_A + B_At + 56 * m
-    rest = (n_z + n_refin) * (2 * B_A + B_At + 16 * n) + n_hp * B_H + niter * 72 * n
-    total = inner_iters * B_in + rest
-    survey = inner_iters * B_in_survey + rest
-    return total, survey, dict(B_H=B_H, B_A=B_A, B_At=B_At, B_M=B_M, B_in=B_in,
-                               B_in_survey=B_in_survey)
+    n_y = 1 if has_b else 0                      # x = Y(-b): the only non-Z solve of a launch
+    n_z = n_solves - n_y
+    z_products = 2 * B_A + B_At + 8 * n
+    parts = dict(B_H=B_H, B_A=B_A, B_At=B_At, B_M=B_M, B_in_survey=B_in_survey)
+    if n_sweeps > 0:
+        B_sweep = 160 * m
+        solves = n_sweeps * B_sweep + n_y * (B_M + 8 * m)
+        refin = n_refin * (B_At + 8 * n + B_A)
+        parts.update(B_sweep=B_sweep, B_in=B_sweep, B_Z=z_products + B_sweep)
+    else:
+        B_in = B_M + 72 * m if nnzM > 0 else B_A + B_At + 8 * m + 72 * m
+        solves = inner_iters * B_in
+        refin = n_refin * z_products
+        parts.update(B_in=B_in)
+    rest = n_z * z_products + n_y * (24 * m + B_At) + n_hp * B_H + niter * 72 * n
+    total = solves + refin + rest
+    survey = (n_solves + n_refin) * 35 * B_in_survey + (n_z + n_refin) * (z_products + 8 * n) \
+        + n_hp * B_H + niter * 72 * n
+    return total, survey, parts
 
 
 class ClockSampler:
@@ -189,33 +207,42 @@ def end_to_end_solve(n, hot_path=None):
 
 
 def run_reference(args):
-    """--impl reference: the CPU path on the host cores (rank 0 only)."""
+    """--impl reference: the CPU path on the host cores (rank 0 only).  The
+    reference factorises with SuperLU, which fails at the headline size (n =
+    1e7: ``factorized`` raises, the dense fallback then needs 364 TiB --
+    profiles/r3_reference_n1e7.txt), so this arm runs the same workload at
+    ``--cpu-n`` (default 4e6, the largest size SuperLU factorises here) and SAYS SO: ``value`` and ``ms_per_step`` are
+    what was measured at that size, ``config.n`` is that size and
+    ``same_config`` is false.  The GPU arm prints its own measurement at the
+    same size (``reference_config_run``) so the two can be compared on one
+    config; the figure scaled to n = 1e7 is a labelled extra."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_s = args.cpu_n
     its, dt, t_factor = cpu_reference_run(n_s, args.iters, args.steps, args.warmup,
                                           args.pattern, args.kappa)
-    scale = n_s / args.n       # per-iteration cost of the CPU path is O(n)
-    value = its * scale
-    sample = ("oracle port of the reference path (scipy SuperLU AugmentedSystem + "
-              "numpy), n=%d m=%d window A, %d forced iterations/step; the "
-              "reference cannot factorise n=%d (SuperLU int32 malloc failure), so "
-              "it/s is scaled by n_sample/n = %.3g (its per-iteration cost is "
-              "linear in n for the banded pattern); factorisation %.1f s outside "
-              "the timed region" % (n_s, n_s // 2, args.iters, args.n, scale, t_factor))
+    sample = ("oracle port of the reference path (scipy SuperLU AugmentedSystem + numpy), "
+              "n=%d m=%d window A, %d steps x %d forced iterations in %.1f s; factorisation "
+              "%.1f s outside the timed region; 1 thread for factor/solve/SpMV"
+              % (n_s, n_s // 2, args.steps, args.iters, dt, t_factor))
+    ran = argparse.Namespace(**vars(args))
+    ran.n = n_s
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "impl": "reference", "metric": METRIC, "value": its, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / max(args.steps, 1) / scale,
+        "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(),
-                         "kind": "port", "sample": sample,
-                         "measured_it_per_s_at_sample": its,
-                         "host_cpus": os.cpu_count()},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+        "config": workload_config(ran),
+        "same_config": bool(n_s == args.n),
+        "requested_n": args.n,
+        "extrapolated": {"n": args.n, "value": its * n_s / args.n, "unit": UNIT,
+                         "how": "per-iteration cost of the CPU path is linear in n for the "
+                                "windowed pattern; NOT a measurement"},
+        "cpu_baseline": {"value": its, "unit": UNIT, "cores": host_threads(),
+                         "kind": "port", "sample": sample, "host_cpus": os.cpu_count()},
+        "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -227,12 +254,13 @@ def workload_config(args):
                         "(BASELINE.json metric config): n=%d, m=%d, H banded SPD "
                         "5 nnz/row cond=%g, A %s 3 nnz/row; projected_cg with "
                         "%d forced iterations per step (tol=1e-30, radius=inf), "
-                        "NormalEquation projector via inner CG rtol=%g"
+                        "NormalEquation projector: banded direct solve of A A' "
+                        "(CG fallback), residual tolerance %g"
                         % (args.n, args.n // 2, args.kappa, args.pattern,
                            args.iters, args.inner_rtol),
             "n": args.n, "m": args.n // 2, "iters_per_step": args.iters,
             "pattern": args.pattern, "inner_rtol": args.inner_rtol,
-            "l2": "working set per inner iteration (~0.7 GB at n=1e7) exceeds "
+            "l2": "working set per outer iteration (~3.4 GB at n=1e7) exceeds "
                   "the 126 MB L2; no explicit flush",
             "parallelism": "1 GPU" if args.gpus == 1 else "row-partitioned x%d" % args.gpus}
 
@@ -244,6 +272,54 @@ def peaks():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def x_checksum(x):
+    """Order-independent fingerprint of the solution, printed by every N so
+    that the driver's own records show N-GPU = 1-GPU: ||x||_2, sum(x) and a
+    weighted sum with a fixed pseudo-random weight vector."""
+    x = np.asarray(x, dtype=np.float64)
+    w = np.cos(np.arange(x.shape[0], dtype=np.float64) * 0.618033988749895)
+    return {"norm2": float(np.linalg.norm(x)), "sum": float(x.sum()),
+            "weighted": float(np.dot(w, x)), "n": int(x.shape[0])}
+
+
+def gpu_run_at(n, args):
+    """The GPU arm on the config the reference arm can run (``--cpu-n``): the same
+    measurement as the headline (device-resident it/s and e2e with host vectors),
+    so that GPU and CPU can be compared on ONE config."""
+    from ipsolver_b200 import synthetic, device
+    from ipsolver_b200.projections import projections
+    from ipsolver_b200.qp_subproblem import projected_cg, HessianOperator
+    m = n // 2
+    H, A, c, b = synthetic.make_qp(n, args.pattern, args.kappa, seed=0)
+    ctx = device.Context.default()
+    Z, LS, Y = projections(A)
+    Hop = HessianOperator(n, [H])
+    Hd = Hop.device
+    proj = Z.projector
+    dc, db = device.DeviceVector(ctx, c), device.DeviceVector(ctx, b)
+    dx = device.DeviceVector(ctx, length=n)
+    for _ in range(3):
+        device.projected_cg_dev(proj, Hd, dc, db, dx, tol=1e-30, max_iter=args.iters)
+    steps = max(args.steps, 5)
+    ctx.timer_start()
+    for _ in range(steps):
+        info = device.projected_cg_dev(proj, Hd, dc, db, dx, tol=1e-30, max_iter=args.iters)
+    ms = ctx.timer_stop()
+    for _ in range(2):
+        projected_cg(Hop, c, Z, Y, b, tol=1e-30, max_iter=args.iters)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        projected_cg(Hop, c, Z, Y, b, tol=1e-30, max_iter=args.iters)
+    t_e2e = time.perf_counter() - t0
+    return {"n": n, "m": m, "steps": steps, "iters_per_step": args.iters,
+            "value": steps * int(info.niter) / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms / steps,
+            "e2e": {"value": steps * int(info.niter) / t_e2e, "unit": UNIT,
+                    "ms_per_step": 1e3 * t_e2e / steps,
+                    "note": "pageable numpy c, b in, x out"},
+            "what": "this arm on the config `bench.py --impl reference` runs"}
 
 
 def run_b200(args):
@@ -292,47 +368,85 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (the persistent solve kernel)
     i0 = infos[-1]
-    has_b = 1
-    n_z = int(i0.n_solves) - int(i0.n_refinements) - has_b
     nnzM = proj.aat_nnz
+    band = proj.band_info
     bytes_launch, bytes_survey, parts = algorithmic_bytes(
-        n, m, H.nnz, A.nnz, nnzM, int(i0.niter), int(i0.inner_iters), n_z,
-        int(i0.n_refinements), int(i0.n_spmv_h))
+        n, m, H.nnz, A.nnz, nnzM, int(i0.niter), int(i0.inner_iters), int(i0.n_solves),
+        int(i0.n_refinements), int(i0.n_spmv_h), int(i0.n_sweeps))
     avg_ms = float(np.mean(kernel_ms))
     peak, peak_src = peaks()
     achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_projected_cg_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("k_projected_cg_bytes_per_launch")
+            traffic_src = ("NOT measured in this run: ncu --set full capture of the same "
+                           "command, committed as profiles/traffic.json (%s)" % tj.get("source", "?"))
         except Exception:
             traffic = None
+    if int(i0.n_sweeps) > 0:
+        model = ("as run: (A A')^-1 by the banded direct solve (half-bandwidth %d, chunks of %d "
+                 "rows + %d overlap), B_sweep = 160 m; Z applies verified by their "
+                 "orthogonality product, the Y solve by one product with M (nnzM = %d)"
+                 % (band["bandwidth"], band["chunk_rows"], band["overlap"], nnzM))
+    elif nnzM > 0:
+        model = "as run: inner CG on the explicit product M = A A' (nnzM = %d), B_in = B_M + 72 m" % nnzM
+    else:
+        model = "as run: inner CG applies A' then A, B_in = B_A + B_At + 80 m"
     roofline = {"bound": "hbm", "kernel": "k_projected_cg (persistent cooperative)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_launch,
-                "bytes_model": "as run: inner CG on the explicit product M = A A' "
-                               "(nnzM = %d), B_in = B_M + 72 m" % nnzM if nnzM > 0 else
-                               "as run: inner CG applies A' then A, B_in = B_A + B_At + 80 m",
+                "bytes_model": model,
                 "avg_launch_ms": avg_ms,
                 "inner_iters_per_launch": int(i0.inner_iters),
                 "inner_iters_per_projection": int(i0.inner_iters) / max(int(i0.n_solves), 1),
+                "solves_per_launch": int(i0.n_solves), "sweeps_per_launch": int(i0.n_sweeps),
+                "refinements_per_launch": int(i0.n_refinements),
+                "cg_fallbacks_per_launch": int(i0.n_fallbacks),
+                "band": band,
                 "bytes_per_unit": parts,
                 "survey_8d_model": {
                     "algorithmic_bytes_per_launch": bytes_survey,
                     "effective_GBs": bytes_survey / (avg_ms * 1e-3) / 1e9,
                     "effective_frac": bytes_survey / (avg_ms * 1e-3) / 1e9 / peak,
-                    "note": "same launch priced with SURVEY.md 8d's two-SpMV formulation "
-                            "(B_in = B_A + B_At + 56 m); exceeds `achieved` because the "
-                            "explicit product moves fewer bytes per inner iteration"}}
+                    "note": "same launch priced with SURVEY.md 8d's formulation (an inner CG of "
+                            "35 iterations per solve, B_in = B_A + B_At + 56 m): the traffic "
+                            "the path would need without the direct solve -- a speed-up "
+                            "figure, not a roofline fraction"}}
 
-    # inner CG iteration in isolation (same device code, fixed count)
-    inner_ms = device.bench_inner_iterations(proj, dc, 50)
-    inner_ms = device.bench_inner_iterations(proj, dc, 50)
-    roofline["inner_iteration_us"] = 1e3 * inner_ms / 51
-    roofline["inner_iteration_GBs"] = parts["B_in"] / (inner_ms * 1e-3 / 51) / 1e9
+    # phase timeline of one launch: %globaltimer at every grid barrier (CTA 0)
+    try:
+        ctx.trace(4096)
+        device.projected_cg_dev(proj, Hd, dc, db, dx, tol=1e-30, max_iter=args.iters)
+        stamps = ctx.trace_read().astype(np.int64)
+        ctx.trace(0)
+        d_us = np.diff(stamps) / 1e3
+        per_it = 7 if int(i0.n_sweeps) > 0 else None
+        tl = {"barriers": int(len(stamps)), "sum_ms": float(d_us.sum() / 1e3)}
+        if per_it and len(d_us) >= per_it * int(i0.niter):
+            last = d_us[-per_it * int(i0.niter):].reshape(int(i0.niter), per_it)
+            names = ["x+=alpha p; r+=alpha Hp", "rhs = A~ r", "banded sweep", "g = r - A~' v",
+                     "A g (orthogonality)", "p = -g + beta p", "H p"]
+            tl["per_iteration_us"] = {k: float(v) for k, v in zip(names, np.median(last, axis=0))}
+        roofline["timeline"] = tl
+    except Exception as exc:          # measurement aid only
+        roofline["timeline"] = {"error": str(exc)}
+
+    # the (A A')^-1 sweep in isolation (same device code, repeated inside one launch)
+    if band["in_use"]:
+        device.bench_phase(proj, 9, 3)
+        sw_ms = min(device.bench_phase(proj, 9, 20) for _ in range(3)) / 20
+        roofline["sweep_us"] = 1e3 * sw_ms
+        roofline["sweep_GBs"] = parts["B_sweep"] / (sw_ms * 1e-3) / 1e9
+    else:
+        inner_ms = device.bench_inner_iterations(proj, dc, 50)
+        inner_ms = device.bench_inner_iterations(proj, dc, 50)
+        roofline["inner_iteration_us"] = 1e3 * inner_ms / 51
+        roofline["inner_iteration_GBs"] = parts["B_in"] / (inner_ms * 1e-3 / 51) / 1e9
 
     # ---- e2e: host vectors through the public API
     hc = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
@@ -356,21 +470,23 @@ def run_b200(args):
     xd = dx.download()
     same = float(np.linalg.norm(xd - x_e2e) / max(np.linalg.norm(xd), 1e-300))
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1)
-    cpu = None
+    # ---- CPU baseline on a bounded sample (rank 0, N=1), and the GPU on that sample
+    cpu, ref_cfg = None, None
     if not args.no_cpu:
         its, dt, t_factor = cpu_reference_run(args.cpu_n, args.iters, args.cpu_steps, 0,
                                               args.pattern, args.kappa)
-        scale = args.cpu_n / n
-        cpu = {"value": its * scale, "unit": UNIT, "cores": host_threads(),
+        cpu = {"value": its, "unit": UNIT, "cores": host_threads(),
                "kind": "port",
-               "sample": "oracle (scipy SuperLU AugmentedSystem + numpy) at n=%d, "
-                         "%d steps x %d forced iterations, %.1f s timed + %.1f s "
-                         "factorisation; scaled by n_sample/n=%.3g to this workload "
-                         "(the reference cannot factorise n=1e7: SuperLU int32 malloc "
-                         "failure)" % (args.cpu_n, args.cpu_steps, args.iters, dt,
-                                       t_factor, scale),
-               "measured_it_per_s_at_sample": its, "host_cpus": os.cpu_count()}
+               "sample": "oracle (scipy SuperLU AugmentedSystem + numpy) on the same workload "
+                         "at n=%d (the reference cannot factorise n=%d: SuperLU fails, "
+                         "profiles/r3_reference_n1e7.txt): %d steps x %d forced iterations, "
+                         "%.1f s timed + %.1f s factorisation; value is the MEASURED it/s at "
+                         "that size" % (args.cpu_n, n, args.cpu_steps, args.iters, dt, t_factor),
+               "n": args.cpu_n, "host_cpus": os.cpu_count(),
+               "extrapolated_to_workload": {"value": its * args.cpu_n / n, "unit": UNIT,
+                                            "how": "x n_sample/n (cost per iteration linear in n); "
+                                                   "not a measurement"}}
+        ref_cfg = gpu_run_at(args.cpu_n, args)
 
     # ---- end-to-end solve (BASELINE config 2: n = 1e6 through the SQP outer loop)
     solve = None
@@ -391,10 +507,13 @@ def run_b200(args):
         "data": "synthetic", "config": workload_config(args),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
+        "reference_config_run": ref_cfg,
         "setup_s": {"generate": t_gen, "upload_and_transpose": t_setup},
         "end_to_end_solve": solve,
         "grid": dict(zip(("blocks", "threads", "sms"), ctx.grid())),
         "e2e_vs_resident_rel_diff": same,
+        "result_check": {"rel_feasibility": float(np.linalg.norm(A.dot(xd) + b) / np.linalg.norm(b)),
+                         "x_checksum": x_checksum(xd)},
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -497,20 +616,39 @@ def run_b200_dist(args):
                            dtype=torch.int64, device="cuda")
     dist.all_reduce(nnz_loc)
     nnzM, nnzH, nnzA = (int(v) for v in nnz_loc.tolist())
-    n_z = int(i0.n_solves) - int(i0.n_refinements) - 1
     bytes_launch, bytes_survey, parts = algorithmic_bytes(
-        n, m, nnzH, nnzA, nnzM, int(i0.niter), int(i0.inner_iters), n_z,
-        int(i0.n_refinements), int(i0.n_spmv_h))
+        n, m, nnzH, nnzA, nnzM, int(i0.niter), int(i0.inner_iters), int(i0.n_solves),
+        int(i0.n_refinements), int(i0.n_spmv_h), int(i0.n_sweeps))
     t = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     avg_ms = float(t.item())
     peak, peak_src = peaks()
     achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
+    # phase timeline of one launch on rank 0 (%globaltimer at every grid barrier)
+    timeline = None
+    try:
+        ctx.trace(4096)
+        sync_all()
+        inf_t = S.projected_cg(dc, db, dx, tol=1e-30, max_iter=args.iters)
+        stamps = ctx.trace_read().astype(np.int64)
+        ctx.trace(0)
+        d_us = np.diff(stamps) / 1e3
+        timeline = {"barriers": int(len(stamps)), "sum_ms": float(d_us.sum() / 1e3),
+                    "kernel_ms": float(inf_t.kernel_ms)}
+        if int(i0.n_sweeps) > 0 and len(d_us) >= 7 * int(i0.niter):
+            last = d_us[-7 * int(i0.niter):].reshape(int(i0.niter), 7)
+            names = ["x+=alpha p; r+=alpha Hp", "rhs = A~ r", "banded sweep", "g = r - A~' v",
+                     "A g (orthogonality)", "p = -g + beta p", "H p"]
+            timeline["per_iteration_us"] = {k: float(v) for k, v in zip(names, np.median(last, axis=0))}
+    except Exception as exc:
+        timeline = {"error": str(exc)}
     if hashed:
         feas = None            # nobody holds the whole A; parity is scripts/dist_check.py's job
+        x_all = S.gather(dx.download())
     else:
         x_all = S.gather(dx.download())
         feas = float(np.linalg.norm(A.dot(x_all) + b) / np.linalg.norm(b))
+    checksum = x_checksum(x_all)
     if rank == 0:
         cfg = workload_config(args)
         line = {
@@ -533,15 +671,20 @@ def run_b200_dist(args):
                          "algorithmic_bytes_per_launch": bytes_launch,
                          "avg_launch_ms": avg_ms,
                          "inner_iters_per_launch": int(i0.inner_iters),
+                         "sweeps_per_launch": int(i0.n_sweeps),
+                         "cg_fallbacks_per_launch": int(i0.n_fallbacks),
+                         "banded_direct_solve": bool(S.band),
+                         "timeline_rank0": timeline,
                          "bytes_per_unit": parts},
             "cpu_baseline": None,
             "comm": {"data_path": "in-kernel NVLink peer-memory stores + flag barriers "
                                   "(no NCCL call inside the timed region)",
                      "ghosts_per_rank": {"n_space": [len(g) for g in S.parts["ghosts"][0]],
                                          "m_space": [len(g) for g in S.parts["ghosts"][1]]},
-                     "global_syncs_per_inner_iteration": 2},
+                     "cross_gpu_reductions_per_outer_iteration": 3,
+                     "halo_exchanges_per_outer_iteration": 5},
             "setup_s": {"generate": t_gen, "partition_upload_connect": t_setup},
-            "result_check": {"rel_feasibility": feas},
+            "result_check": {"rel_feasibility": feas, "x_checksum": checksum},
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
@@ -562,7 +705,7 @@ def main():
     ap.add_argument("--pattern", default="window")
     ap.add_argument("--kappa", type=float, default=1e4)
     ap.add_argument("--inner-rtol", type=float, default=1e-13)
-    ap.add_argument("--cpu-n", type=int, default=1_000_000)
+    ap.add_argument("--cpu-n", type=int, default=4_000_000)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--solve-n", type=int, default=1_000_000,

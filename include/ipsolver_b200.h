@@ -60,6 +60,9 @@ typedef struct {
     double  max_orth;         /* largest orthogonality() accepted                */
     double  tol_used;         /* tolerance actually used (default rule :530)     */
     double  kernel_ms;        /* device time of the solve kernel (CUDA events)   */
+    int64_t n_sweeps;         /* sweeps of the banded direct solve (0: CG only)  */
+    int32_t n_fallbacks;      /* banded solves given up for the CG (0 normally)  */
+    int32_t reserved;
 } ipb_pcg_info;
 
 /* Counters of one projector application (Z, LS or Y). */

@@ -1247,6 +1247,7 @@ static int run_pcg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, const double *d
         info->n_solves = h->n_solves; info->n_refinements = h->n_refinements;
         info->n_spmv_h = h->n_spmv_h; info->max_orth = h->max_orth;
         info->tol_used = h->tol_used; info->kernel_ms = ms;
+        info->n_sweeps = h->n_sweeps; info->n_fallbacks = h->n_fallbacks; info->reserved = 0;
     }
     if (h->status == IPB_ERR_TR_INFEASIBLE)
         IPB_FAIL(ctx, IPB_ERR_TR_INFEASIBLE, "Trust region problem does not have a solution.");

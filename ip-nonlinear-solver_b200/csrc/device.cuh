@@ -293,7 +293,8 @@ struct __align__(128) Smem {
     unsigned gseq;                // cross-GPU sequence number (multi-GPU only)
     unsigned ghost_seq;           // sequence number the ghost zone of the current product carries
     unsigned phase;               // grid barriers passed so far (parity selects the partials buffer)
-    unsigned long long bfull[WARPS * 4];  // banded sweep: mbarriers of the per-warp rings of step buffers
+    unsigned long long bfull[8];          // banded sweep: "full" mbarriers of the 8 block buffers
+    unsigned long long bempty[8];         // ... and their "released" mbarriers
     unsigned bseq[WARPS];         // ring uses of each warp so far
     double red[WARPS];
     double out[NSLOT];
@@ -350,8 +351,10 @@ __device__ __forceinline__ void pipeline_init(Smem &sm, const SyncView &S) {
         sm.seq = 0;
         sm.phase = 0;
         for (int w = 0; w < WARPS; ++w) sm.bseq[w] = 0;
-        for (int q = 0; q < WARPS * 4; ++q)
+        for (int q = 0; q < 8; ++q) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.bfull[q])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.bempty[q])));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -957,32 +960,37 @@ __device__ __forceinline__ void ld4_guard(const double *v, int row, int lo, int 
     }
 }
 
-// ---- per-warp ring of sweep steps.  One step = the factor rows of the warp's
-// 32 chunks, [HB][32] doubles = 2 KB contiguous in HBM, landed by one TMA bulk
-// copy on the buffer's mbarrier.  All addresses are 32-bit shared-window
-// addresses kept incrementally: the step loop is instruction-bound when few
-// warps per SM are active, so its bookkeeping is pared down to a few
-// integer instructions.
+// ---- rings of sweep blocks.  One step = the factor rows of a warp's 32
+// chunks, [HB][32] doubles = 2 KB; a BLOCK = 4 consecutive steps = 8 KB
+// contiguous in HBM, landed by ONE TMA bulk copy on the block's "full"
+// mbarrier (a thread issues only ~3 bulk copies per microsecond, so a copy
+// per step would cap a warp at 3 steps/us).  Warps 0..3 of a CTA consume
+// (thread = chunk), warp w + 4 produces for warp w: it waits for a buffer's
+// "released" mbarrier and issues the next copy, so neither the wait nor the
+// issue is on the consumer's step-to-step path.  The 8 buffers (64 KB of the
+// stages) are shared by the consumer warps that have a group at all: 8, 4 or
+// 2 blocks deep.  All addresses are 32-bit shared-window addresses.
+constexpr int BAND_STEP = HB * 32;                 // doubles per step
+constexpr int BAND_BLK = 4 * BAND_STEP;            // doubles per block
+constexpr int BAND_CW = WARPS / 2;                 // consumer warps per CTA
+
 struct BandRing {
-    unsigned data;      // shared address of buffer 0, this lane's column (+ lane * 8)
-    unsigned bars;      // shared address of the mbarrier of buffer 0
-    unsigned mask;      // NB - 1
-    unsigned b, par;    // buffer and phase parity of the next step to consume
+    unsigned data;      // shared address of buffer 0 (+ lane * 8 for a consumer)
+    unsigned fulls;     // shared address of the "full" mbarrier of buffer 0
+    unsigned empties;   // shared address of the "released" mbarrier of buffer 0
+    unsigned mask;      // depth - 1 (depth a power of two)
 };
 
-__device__ __forceinline__ void ring_issue(const BandRing &R, unsigned buf, const double *src) {
-    // The buffer was last READ through the generic proxy by the lanes of this
-    // warp and the __syncwarp() before this call orders those reads before the
-    // copy (consumer release / producer acquire of a TMA pipeline; a proxy
-    // fence is for generic WRITES the async proxy must see and would cost
-    // hundreds of cycles per step here).
-    constexpr unsigned BYTES = HB * 32 * sizeof(double);
-    const unsigned bar = R.bars + buf * 8u;
-    const unsigned dst = R.data + buf * BYTES;          // lane 0 only: its column is the buffer start
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BYTES) : "memory");
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(dst), "l"(src), "r"(BYTES), "r"(bar) : "memory");
+__device__ __forceinline__ void mbar_wait_s(unsigned bar, unsigned parity, int *abort_flag) {
+    unsigned spins = 0, done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 24)) { *abort_flag = 6; __trap(); }
+    } while (!done);
 }
 
 template <int OFF>
@@ -994,49 +1002,62 @@ __device__ __forceinline__ double lds_off(unsigned addr) {
 
 struct BandRow { double l0, l1, l2, l3, l4, l5, l6, l7; };
 
-// wait for the next step of the ring, read this lane's factor row, advance
-__device__ __forceinline__ BandRow ring_next(BandRing &R, int *abort_flag) {
-    const unsigned bar = R.bars + R.b * 8u;
-    unsigned spins = 0, done;
-    do {
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(done) : "r"(bar), "r"(R.par) : "memory");
-        if (!done && ++spins > (1u << 24)) { *abort_flag = 6; __trap(); }
-    } while (!done);
-    const unsigned a = R.data + R.b * (unsigned)(HB * 32 * sizeof(double));
+template <int Q>
+__device__ __forceinline__ BandRow band_row(unsigned a) {       // step Q of the block at ``a``
+    constexpr int O = Q * BAND_STEP * 8;
     BandRow r;
-    r.l0 = lds_off<0>(a);    r.l1 = lds_off<256>(a);  r.l2 = lds_off<512>(a);  r.l3 = lds_off<768>(a);
-    r.l4 = lds_off<1024>(a); r.l5 = lds_off<1280>(a); r.l6 = lds_off<1536>(a); r.l7 = lds_off<1792>(a);
-    R.b = (R.b + 1u) & R.mask;
-    R.par ^= (R.b == 0u);
+    r.l0 = lds_off<O>(a);        r.l1 = lds_off<O + 256>(a);  r.l2 = lds_off<O + 512>(a);
+    r.l3 = lds_off<O + 768>(a);  r.l4 = lds_off<O + 1024>(a); r.l5 = lds_off<O + 1280>(a);
+    r.l6 = lds_off<O + 1536>(a); r.l7 = lds_off<O + 1792>(a);
     return r;
 }
+
+// y_j = (r_j - sum_k L[j][j-k] y_{j-k}) / L_jj; y_{j-1} enters last, so only one
+// multiply-add and one multiply lie between consecutive steps
+#define IPB_FWD_STEP(Q)                                                              \
+    {                                                                                \
+        const BandRow L = band_row<Q>(a);                                            \
+        const double pa = __fma_rn(L.l7, y7, __fma_rn(L.l5, y5, L.l3 * y3));         \
+        const double pb = __fma_rn(L.l6, y6, __fma_rn(L.l4, y4, L.l2 * y2));         \
+        const double t = __fma_rn(-L.l1, y1, rc[Q] - (pa + pb));                     \
+        const double y = t * L.l0;                                                   \
+        y7 = y6; y6 = y5; y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;                \
+        if (keep) yp[Q * 32] = y;                                                    \
+        if (own) ss += rc[Q] * rc[Q];                                                \
+    }
+
+// z_j = (y_j - c0) / L_jj, then row j's entries scatter into the rows above it;
+// c_k: what the rows already done contribute to row j-k
+#define IPB_BWD_STEP(Q)                                                              \
+    {                                                                                \
+        const BandRow L = band_row<Q>(a);                                            \
+        const double z = (yc[Q] - c0) * L.l0;                                        \
+        c0 = __fma_rn(L.l1, z, c1);                                                  \
+        c1 = __fma_rn(L.l2, z, c2);                                                  \
+        c2 = __fma_rn(L.l3, z, c3);                                                  \
+        c3 = __fma_rn(L.l4, z, c4);                                                  \
+        c4 = __fma_rn(L.l5, z, c5);                                                  \
+        c5 = __fma_rn(L.l6, z, c6);                                                  \
+        c6 = L.l7 * z;                                                               \
+        zo[Q] = z;                                                                   \
+    }
 
 // out (+)= L^-T L^-1 in, chunk by chunk (see BandView).  Thread = chunk: a
 // forward substitution over the chunk's B + 2 ov rows from a zero start, the
 // result of rows >= ov kept in Bd.y, then the backward substitution down to
-// the first owned row; only the B owned rows are written.  The factor rows of
-// the warp's 32 chunks arrive step by step through a ring of TMA bulk copies
-// (4 to 16 deep), so no registers hold loads in flight and the 2 KB blocks are
-// read from HBM fully coalesced; the recurrences are arranged so that only one
-// multiply-add and one multiply lie between consecutive steps.
-// Returns this thread's share of ||in||^2 (owned rows).  ``in`` and ``out``
-// must not alias.
+// the first owned row; only the B owned rows are written.  Returns this
+// thread's share of ||in||^2 (owned rows).  ``in`` and ``out`` must not alias.
 __device__ __noinline__ double band_sweep(const ProjView &P, const SyncView &S, Smem &sm,
                                           const double *in, double *out, int accumulate) {
     const BandView &Bd = P.band;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m = P.m, B = Bd.B, ov = Bd.ov, steps = Bd.steps;
-    // ring depth: the WARPS * 4 step buffers (64 KB of the stages) are shared by
-    // the warps of the CTA that have a group at all -- few groups per CTA (large
-    // chunks, or a small / row-partitioned problem) get deep rings, so the bulk
-    // copies in flight still cover the HBM latency
-    const int wact = max(1, min(WARPS, (Bd.ngroup + (int)gridDim.x - 1) / (int)gridDim.x));
-    const int NB = wact <= 2 ? 16 : (wact <= 4 ? 8 : 4);
-    constexpr int STEP = HB * 32;          // doubles per step
+    const int nfb = steps / 4, nbb = (steps - ov) / 4;        // forward / backward blocks of a group
+    // consumer warps of this CTA that have a group at all share the 8 buffers
+    const int wact = max(1, min(BAND_CW, (Bd.ngroup + (int)gridDim.x - 1) / (int)gridDim.x));
+    const int depth = wact == 1 ? 8 : (wact == 2 ? 4 : 2);
+    const bool producer = warp >= BAND_CW;
+    const int cw = producer ? warp - BAND_CW : warp;             // the ring this warp works on
     const int in_lo = Bd.in_lo, in_hi = Bd.in_hi;
     double ss = 0.0;
     // row-partitioned: the neighbours' rows next to the own block are ghosts of
@@ -1045,76 +1066,68 @@ __device__ __noinline__ double band_sweep(const ProjView &P, const SyncView &S, 
     if (dist) halo_sync(S, sm, in, 1);
     __syncthreads();                       // the stages are free (previous phase of this CTA is over)
     BandRing R;
-    R.data = smem_addr(reinterpret_cast<double *>(&sm.st[0]) + (size_t)warp * (NB * STEP)) + lane * 8u;
-    R.bars = smem_addr(sm.bfull + warp * NB);
-    R.mask = (unsigned)NB - 1u;
-    {
-        const unsigned useq = sm.bseq[warp];
-        R.b = useq & R.mask;
-        R.par = (useq / (unsigned)NB) & 1u;
+    R.data = smem_addr(reinterpret_cast<double *>(&sm.st[0]) + (size_t)cw * (depth * BAND_BLK));
+    R.fulls = smem_addr(sm.bfull + cw * depth);
+    R.empties = smem_addr(sm.bempty + cw * depth);
+    R.mask = (unsigned)depth - 1u;
+    unsigned u = sm.bseq[cw];              // blocks this ring has carried so far
+    const int gstride = (int)gridDim.x * BAND_CW;
+    if (producer) {
+        // ---- feed the ring of warp cw: forward blocks in order, then the backward ones
+        if (lane == 0 && cw < wact) {
+            constexpr unsigned BYTES = BAND_BLK * sizeof(double);
+            for (int g = (int)blockIdx.x + (int)gridDim.x * cw; g < Bd.ngroup; g += gstride) {
+                const double *Lg = Bd.L + (size_t)g * steps * BAND_STEP;
+                for (int k = 0; k < nfb + nbb; ++k, ++u) {
+                    const double *src = Lg + (size_t)(k < nfb ? k : (nfb - 1 - (k - nfb))) * BAND_BLK;
+                    const unsigned buf = u & R.mask;
+                    // round r of a buffer waits for the release of round r-1 (round 0 passes)
+                    mbar_wait_s(R.empties + buf * 8u, ((u / (unsigned)depth) & 1u) ^ 1u, S.abort_flag);
+                    const unsigned bar = R.fulls + buf * 8u;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                                 ::"r"(bar), "r"(BYTES) : "memory");
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                        ::"r"(R.data + buf * BYTES), "l"(src), "r"(BYTES), "r"(bar) : "memory");
+                }
+            }
+        }
+        __syncthreads();
+        return 0.0;
     }
-    unsigned used = 0;
-    for (int g = (int)blockIdx.x + (int)gridDim.x * warp; g < Bd.ngroup; g += (int)gridDim.x * WARPS) {
-        const double *Lg = Bd.L + (size_t)g * steps * STEP;
+    R.data += lane * 8u;
+    const unsigned u0 = u;
+    for (int g = (int)blockIdx.x + (int)gridDim.x * warp; g < Bd.ngroup; g += gstride) {
         const int e0 = (g * 32 + lane) * B - ov;                       // row of step 0
         double *yp = Bd.y + (size_t)g * (B + ov) * 32 + lane;          // forward result of row e0 + ov
         if (dist && (g == 0 || g == Bd.ngroup - 1)) ghost_wait(S, sm, 1);
         // ================= forward: steps 0 .. steps-1
         {
-            __syncwarp();
-            const double *src = Lg;
-            int left = steps;                                          // steps not yet requested
-            if (lane == 0)
-                for (int q = 0; q < NB && left > 0; ++q, --left, src += STEP)
-                    ring_issue(R, (R.b + q) & R.mask, src);
-            left = max(0, steps - NB); src = Lg + (size_t)min(steps, NB) * STEP;
             double y1 = 0, y2 = 0, y3 = 0, y4 = 0, y5 = 0, y6 = 0, y7 = 0;
             double rn[4];
             ld4_guard(in, e0, in_lo, in_hi, rn);
-            unsigned freed = 0;
-            for (int jb = 0; jb < steps; jb += 4) {
+            for (int jb = 0; jb < steps; jb += 4, ++u) {
                 const double rc[4] = {rn[0], rn[1], rn[2], rn[3]};
                 if (jb + 4 < steps) ld4_guard(in, e0 + jb + 4, in_lo, in_hi, rn);
                 const bool keep = jb >= ov, own = keep && jb < ov + B;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    __syncwarp();           // every lane has read the row of the previous step
-                    if (lane == 0 && (jb | q) != 0 && left > 0) {
-                        ring_issue(R, freed, src);
-                        src += STEP; --left;
-                    }
-                    freed = R.b;
-                    const BandRow L = ring_next(R, S.abort_flag);
-                    // y_j = (r_j - sum_k L[j][j-k] y_{j-k}) / L_jj; y_{j-1} enters last
-                    const double pa = __fma_rn(L.l7, y7, __fma_rn(L.l5, y5, L.l3 * y3));
-                    const double pb = __fma_rn(L.l6, y6, __fma_rn(L.l4, y4, L.l2 * y2));
-                    const double t = __fma_rn(-L.l1, y1, rc[q] - (pa + pb));
-                    const double y = t * L.l0;
-                    y7 = y6; y6 = y5; y5 = y4; y4 = y3; y3 = y2; y2 = y1; y1 = y;
-                    if (keep) { *yp = y; yp += 32; }
-                    if (own) ss += rc[q] * rc[q];
-                }
+                const unsigned buf = u & R.mask;
+                mbar_wait_s(R.fulls + buf * 8u, (u / (unsigned)depth) & 1u, S.abort_flag);
+                const unsigned a = R.data + buf * (unsigned)(BAND_BLK * sizeof(double));
+                IPB_FWD_STEP(0) IPB_FWD_STEP(1) IPB_FWD_STEP(2) IPB_FWD_STEP(3)
+                if (keep) yp += 4 * 32;
+                __syncwarp();               // every lane has read the block: hand the buffer back
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(R.empties + buf * 8u) : "memory");
             }
-            used += (unsigned)steps;
         }
         // ================= backward: steps steps-1 .. ov
         {
-            const int nst = steps - ov;
-            __syncwarp();
-            const double *src = Lg + (size_t)(steps - 1) * STEP;
-            int left = nst;
-            if (lane == 0)
-                for (int q = 0; q < NB && left > 0; ++q, --left, src -= STEP)
-                    ring_issue(R, (R.b + q) & R.mask, src);
-            left = max(0, nst - NB); src = Lg + (size_t)(steps - 1 - min(nst, NB)) * STEP;
-            // c_k: what the rows above contribute to row j-k (k = 0: this row)
             double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
             double yn[4];
             yp -= 4 * 32;                   // forward result of the 4 rows of the first block
 #pragma unroll
             for (int q = 0; q < 4; ++q) yn[q] = yp[q * 32];
-            unsigned freed = 0;
-            for (int jb = steps - 4; jb >= ov; jb -= 4) {
+            for (int jb = steps - 4; jb >= ov; jb -= 4, ++u) {
                 const double yc[4] = {yn[0], yn[1], yn[2], yn[3]};
                 if (jb - 4 >= ov) {
                     yp -= 4 * 32;
@@ -1122,36 +1135,24 @@ __device__ __noinline__ double band_sweep(const ProjView &P, const SyncView &S, 
                     for (int q = 0; q < 4; ++q) yn[q] = yp[q * 32];
                 }
                 double zo[4];
-#pragma unroll
-                for (int q = 3; q >= 0; --q) {
-                    __syncwarp();
-                    if (lane == 0 && (jb != steps - 4 || q != 3) && left > 0) {
-                        ring_issue(R, freed, src);
-                        src -= STEP; --left;
-                    }
-                    freed = R.b;
-                    const BandRow L = ring_next(R, S.abort_flag);
-                    const double z = (yc[q] - c0) * L.l0;
-                    c0 = __fma_rn(L.l1, z, c1);
-                    c1 = __fma_rn(L.l2, z, c2);
-                    c2 = __fma_rn(L.l3, z, c3);
-                    c3 = __fma_rn(L.l4, z, c4);
-                    c4 = __fma_rn(L.l5, z, c5);
-                    c5 = __fma_rn(L.l6, z, c6);
-                    c6 = L.l7 * z;
-                    zo[q] = z;
-                }
+                const unsigned buf = u & R.mask;
+                mbar_wait_s(R.fulls + buf * 8u, (u / (unsigned)depth) & 1u, S.abort_flag);
+                const unsigned a = R.data + buf * (unsigned)(BAND_BLK * sizeof(double));
+                IPB_BWD_STEP(3) IPB_BWD_STEP(2) IPB_BWD_STEP(1) IPB_BWD_STEP(0)
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(R.empties + buf * 8u) : "memory");
                 if (jb < ov + B) {
                     const int row = e0 + jb;             // >= 0: an owned row
                     if (row + 3 < m) {
-                        double2 a = make_double2(zo[0], zo[1]), b = make_double2(zo[2], zo[3]);
+                        double2 a2 = make_double2(zo[0], zo[1]), b2 = make_double2(zo[2], zo[3]);
                         if (accumulate) {
                             const double2 pa = *reinterpret_cast<const double2 *>(out + row);
                             const double2 pb = *reinterpret_cast<const double2 *>(out + row + 2);
-                            a.x += pa.x; a.y += pa.y; b.x += pb.x; b.y += pb.y;
+                            a2.x += pa.x; a2.y += pa.y; b2.x += pb.x; b2.y += pb.y;
                         }
-                        *reinterpret_cast<double2 *>(out + row) = a;
-                        *reinterpret_cast<double2 *>(out + row + 2) = b;
+                        *reinterpret_cast<double2 *>(out + row) = a2;
+                        *reinterpret_cast<double2 *>(out + row + 2) = b2;
                     } else {
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
@@ -1159,14 +1160,15 @@ __device__ __noinline__ double band_sweep(const ProjView &P, const SyncView &S, 
                     }
                 }
             }
-            used += (unsigned)nst;
         }
     }
     __syncwarp();
-    if (lane == 0) sm.bseq[warp] += used;
+    if (lane == 0) sm.bseq[warp] += u - u0;
     __syncthreads();
     return ss;
 }
+#undef IPB_FWD_STEP
+#undef IPB_BWD_STEP
 
 // ---------------------------------------------------------------- (A A')^-1
 // w = (A~ A~') r with  acc0 += w.r : one SpMV with the explicit product M

@@ -30,7 +30,9 @@ class PcgInfo(C.Structure):
                 ("n_allvecs", C.c_int32), ("inner_iters", C.c_int64),
                 ("n_solves", C.c_int64), ("n_refinements", C.c_int64),
                 ("n_spmv_h", C.c_int64), ("max_orth", C.c_double),
-                ("tol_used", C.c_double), ("kernel_ms", C.c_double)]
+                ("tol_used", C.c_double), ("kernel_ms", C.c_double),
+                ("n_sweeps", C.c_int64), ("n_fallbacks", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class ProjInfo(C.Structure):

@@ -6,7 +6,8 @@ arguments, same ``state`` fields and counters), re-stated from the algorithm
 (Lalee-Nocedal-Plantenga 1998; Byrd-Hribar-Nocedal 1999, sec. 3) with the
 reference's constants so that iteration counts can be compared.  Every linear
 algebra step -- ``projections``, ``LS.dot``, ``modified_dogleg``,
-``projected_cg``, ``Y.dot``, ``box_intersections`` -- goes to the device
+``projected_cg``, ``Y.dot``, ``box_intersections``, ``A.dot`` / ``A.T.dot`` --
+goes to the device
 through ``ipsolver_b200``; user callbacks (``fun_and_constr``,
 ``grad_and_jac``, ``lagr_hess``) run on the host between those calls.
 
@@ -35,10 +36,19 @@ BOX_NORMAL = 0.5
 
 def device_hot_path():
     from . import projections as _p, qp_subproblem as _q
+
+    def jac_dot(A, Z, x):
+        """``A x`` with the device copy of A that ``Z`` was built from (same
+        row sums, bit for bit, as scipy's csr_matvec)."""
+        return Z.projector.A.matvec(x) if A.shape[0] else np.zeros(0)
+
+    def jac_tdot(A, Z, y):
+        return Z.projector.A.rmatvec(y) if A.shape[0] else np.zeros(A.shape[1])
+
     return SimpleNamespace(projections=_p.projections, projected_cg=_q.projected_cg,
                            modified_dogleg=_q.modified_dogleg,
                            box_intersections=_q.box_intersections,
-                           hessian=_q.HessianOperator)
+                           hessian=_q.HessianOperator, jac_dot=jac_dot, jac_tdot=jac_tdot)
 
 
 def _identity_scaling(x):
@@ -62,9 +72,9 @@ def _next_radius(radius, ratio, step_norm):
     return radius
 
 
-def _record(state, x, v, f, c, b, A, hp):
+def _record(state, x, v, f, c, b, A, hp, Z):
     state.x, state.v, state.fun, state.grad, state.constr, state.jac = x, v, f, c, b, A
-    state.optimality = norm(c + A.T.dot(v), np.inf)
+    state.optimality = norm(c + hp.jac_tdot(A, Z, v), np.inf)
     state.constr_violation = norm(b, np.inf) if len(b) > 0 else 0
 
 
@@ -86,7 +96,7 @@ def equality_constrained_sqp(fun_and_constr, grad_and_jac, lagr_hess,
     S = scaling(x)
     Z, LS, Y = hp.projections(A, factorization_method)      # :81
     v = -LS.dot(c)                                           # least-squares multipliers :83
-    _record(state, x, v, f, c, b, A, hp)
+    _record(state, x, v, f, c, b, A, hp, Z)
     state.niter += 1
     state.trust_radius, state.penalty = radius, penalty
     if return_all:
@@ -107,7 +117,7 @@ def equality_constrained_sqp(fun_and_constr, grad_and_jac, lagr_hess,
         d = dn + dt
         # model and linearised constraint at the step (:138-140)
         q_model = 1 / 2 * (H.dot(d)).dot(d) + c.T.dot(d)
-        lin_constr = A.dot(d) + b
+        lin_constr = hp.jac_dot(A, Z, d) + b
         vpred = max(1e-16, norm(b) - norm(lin_constr))       # (3.52), kept positive
         penalty_before = penalty
         if q_model > 0:
@@ -142,7 +152,7 @@ def equality_constrained_sqp(fun_and_constr, grad_and_jac, lagr_hess,
             Z, LS, Y = hp.projections(A)                     # method dropped here, as in :225
             v = -LS.dot(c)
             need_hessian = True
-            _record(state, x, v, f, c, b, A, hp)
+            _record(state, x, v, f, c, b, A, hp, Z)
         else:                                                # reject (:240-242)
             penalty = penalty_before
             need_hessian = False

@@ -107,7 +107,10 @@ def _inside_box(box, x0, rel=0.01, absol=0.01):
 class _Rows:
     """One user constraint split into equality and inequality rows."""
 
-    def __init__(self, fun, jac, hess, kind, enforce, x0, sparse_jacobian):
+    def __init__(self, fun, jac, hess, kind, enforce, x0, sparse_jacobian, constant_jac=False):
+        # constant_jac: linear / box constraints -- the Jacobian never changes
+        # (reference _canonical_constraint.py:251-265 re-assembles it every time)
+        self.constant_jac = bool(constant_jac)
         f0 = np.atleast_1d(fun(x0))
         self.m = f0.shape[0]
         J0 = jac(x0)
@@ -174,12 +177,12 @@ def _rows_of(constraint, x0, sparse_jacobian):
         else:
             A = A.toarray() if sps.issparse(A) else np.atleast_2d(A)
         return _Rows(lambda x: A.dot(x), lambda x: A, None, constraint.kind,
-                     constraint.enforce_feasibility, x0, sparse_jacobian)
+                     constraint.enforce_feasibility, x0, sparse_jacobian, constant_jac=True)
     if isinstance(constraint, BoxConstraint):
         n = x0.shape[0]
         eye = sps.eye(n).tocsr() if (sparse_jacobian or sparse_jacobian is None) else np.eye(n)
         return _Rows(lambda x: x, lambda x: eye, None, constraint.kind,
-                     constraint.enforce_feasibility, x0, sparse_jacobian)
+                     constraint.enforce_feasibility, x0, sparse_jacobian, constant_jac=True)
     raise ValueError("Unknown Constraint type.")
 
 
@@ -195,6 +198,11 @@ class _Canonical:
                        else bool(sparse_jacobian or sparse_jacobian is None))
         self.enforce_feasibility = (np.hstack([b.enforce for b in blocks]).astype(bool)
                                     if blocks else np.empty(0, dtype=bool))
+        # all constraints linear: the stacked Jacobian is assembled once and the SAME
+        # objects are handed out every time, so projections() recognises them and
+        # neither uploads nor refreshes anything
+        self._constant = bool(blocks) and all(b.constant_jac for b in blocks)
+        self._jac_cache = None
 
     def constr(self, x):
         if not self.blocks:
@@ -203,6 +211,14 @@ class _Canonical:
         return np.hstack([p[0] for p in parts]), np.hstack([p[1] for p in parts])
 
     def jac(self, x):
+        if self._constant and self._jac_cache is not None:
+            return self._jac_cache
+        out = self._assemble_jac(x)
+        if self._constant:
+            self._jac_cache = out
+        return out
+
+    def _assemble_jac(self, x):
         n = self.n_vars
         if not self.blocks:
             empty = sps.csr_matrix((0, n)) if self.sparse else np.empty((0, n))

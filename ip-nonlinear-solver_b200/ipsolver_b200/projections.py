@@ -95,8 +95,31 @@ def orthogonality(A, g):
     return A.orthogonality(np.asarray(g, dtype=np.float64))
 
 
+CACHE_PATTERNS = 4        # device projectors kept per context (least recently used first out)
+
+
+def _fingerprint(A):
+    """Cheap guard against in-place edits of a matrix that is handed in again
+    (the reference's closures hold A by reference, so callers must not mutate
+    it; this catches the common slips without an O(nnz) comparison)."""
+    d = A.data
+    if d.shape[0] == 0:
+        return (0,)
+    step = max(1, d.shape[0] // 1024)
+    return (d.shape[0], float(d[::step].sum()), float(d[0]), float(d[-1]))
+
+
 def _binding_for(A, orth_tol, max_refin):
     ctx = Context.default()
+    A_in = A
+    # the very same host matrix as last time (a LinearConstraint's Jacobian):
+    # nothing to convert, upload or refresh (SURVEY.md 8f-3)
+    last = getattr(ctx, "_last_binding", None)
+    if last is not None and last[0] is A_in and last[2] == (float(orth_tol), int(max_refin),
+                                                          dict(_INNER).__repr__()) \
+            and sps.issparse(A_in) and last[3] == _fingerprint(A_in) \
+            and last[1].projector.version == last[1].version:
+        return last[1]
     A = sps.csr_matrix(A)
     if not A.has_canonical_format:
         A = A.copy()
@@ -109,12 +132,21 @@ def _binding_for(A, orth_tol, max_refin):
               int(_INNER["inner_maxit"]), int(_INNER["aat_mode"]),
               tuple(int(v) for v in _INNER["band"]))
     if cached is not None and cached.params == params and cached.A.same_pattern(A):
+        ctx._pattern_cache[key] = ctx._pattern_cache.pop(key)      # most recently used last
         cached.A.update_values(A.data)
         cached.refresh()
-        return Binding(cached, A)
-    proj = DeviceProjector(ctx, DeviceCSR(ctx, A, True), *params)
-    ctx._pattern_cache[key] = proj
-    return Binding(proj, A)
+        bind = Binding(cached, A)
+    else:
+        proj = DeviceProjector(ctx, DeviceCSR(ctx, A, True), *params)
+        ctx._pattern_cache.pop(key, None)
+        ctx._pattern_cache[key] = proj
+        while len(ctx._pattern_cache) > CACHE_PATTERNS:             # bound the HBM held by the cache
+            ctx._pattern_cache.pop(next(iter(ctx._pattern_cache)))
+        bind = Binding(proj, A)
+    if sps.issparse(A_in):
+        ctx._last_binding = (A_in, bind, (float(orth_tol), int(max_refin), dict(_INNER).__repr__()),
+                             _fingerprint(A_in))
+    return bind
 
 
 def projections(A, method=None, orth_tol=1e-12, max_refin=3, tol=1e-15):

@@ -56,6 +56,8 @@ class HessianOperator(LinearOperator):
         self.dense = dense_sum
         self._ctx = ctx
         self._dev = None
+        self._csr = None
+        self._token = object()
 
     def with_diag_tail(self, diag_tail):
         """``blockdiag(self, diag(diag_tail))`` -- the scaled barrier Hessian
@@ -68,6 +70,7 @@ class HessianOperator(LinearOperator):
         out.n = self.n + out.diag_tail.shape[0]
         LinearOperator.__init__(out, dtype=np.float64, shape=(out.n, out.n))
         out.sparse, out.dense, out._ctx, out._dev = self.sparse, self.dense, self._ctx, None
+        out._csr, out._token = None, object()
         return out
 
     @property
@@ -75,7 +78,10 @@ class HessianOperator(LinearOperator):
         """Device operator.  The CSR term is cached per sparsity pattern on the
         context: a new Hessian with the pattern of the previous one (every outer
         iteration of the SQP / barrier loops) only re-uploads its values instead
-        of rebuilding row blocks and descriptors."""
+        of rebuilding row blocks and descriptors.  The cached matrix remembers
+        which operator wrote its values last: an operator that finds another
+        one's values there uploads its own again before it is applied, so two
+        live operators with one pattern never act for each other."""
         if self._dev is None:
             ctx = self._ctx or Context.default()
             csr = None
@@ -84,15 +90,24 @@ class HessianOperator(LinearOperator):
                 if not S.has_canonical_format:
                     S = S.copy()
                     S.sum_duplicates()
+                    self.sparse = S
                 cache = ctx.__dict__.setdefault("_hess_csr_cache", {})
                 key = (S.shape, S.nnz)
-                csr = cache.get(key)
+                csr = cache.pop(key, None)
                 if csr is not None and csr.same_pattern(S):
                     csr.update_values(S.data)
                 else:
-                    csr = cache[key] = DeviceCSR(ctx, S, with_transpose=False)
+                    csr = DeviceCSR(ctx, S, with_transpose=False)
+                cache[key] = csr                               # most recently used last
+                while len(cache) > 4:
+                    cache.pop(next(iter(cache)))
+                csr.last_writer = self._token
+            self._csr = csr
             self._dev = DeviceHessian(ctx, self.n, self.n_x, csr=csr,
                                       dense=self.dense, diag_tail=self.diag_tail)
+        elif self._csr is not None and self._csr.last_writer is not self._token:
+            self._csr.update_values(self.sparse.data)
+            self._csr.last_writer = self._token
         return self._dev
 
     def _matvec(self, x):

@@ -103,7 +103,8 @@ class BarrierSubproblem:
         stacked = sps.vstack([J_eq, J_ineq], "csr")
         key = (stacked.nnz, stacked.shape)
         if self._pattern is None or self._pattern[0] != key \
-                or not np.array_equal(self._pattern[1], stacked.indices):
+                or not np.array_equal(self._pattern[1], stacked.indices) \
+                or not np.array_equal(self._pattern[5], stacked.indptr):
             extra = np.concatenate((np.zeros(self.n_eq, dtype=np.int64),
                                     np.arange(self.n_ineq + 1, dtype=np.int64)))
             indptr = stacked.indptr.astype(np.int64) + extra
@@ -114,8 +115,9 @@ class BarrierSubproblem:
             indices = np.empty(nnz, dtype=np.int64)
             indices[is_slack] = self.n_vars + np.arange(self.n_ineq)
             indices[~is_slack] = stacked.indices
-            self._pattern = (key, stacked.indices.copy(), indptr, indices, is_slack)
-        _, _, indptr, indices, is_slack = self._pattern
+            self._pattern = (key, stacked.indices.copy(), indptr, indices, is_slack,
+                             stacked.indptr.copy())
+        _, _, indptr, indices, is_slack, _ = self._pattern
         data = np.empty(indices.shape[0])
         data[is_slack] = s
         data[~is_slack] = stacked.data

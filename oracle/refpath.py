@@ -486,4 +486,7 @@ def host_hot_path():
     return SimpleNamespace(
         projections=lambda A, method=None: build_projectors(A, method),
         projected_cg=eqp_projected_cg, modified_dogleg=dogleg_normal_step,
-        box_intersections=segment_box, hessian=HostLagrangianHessian)
+        box_intersections=segment_box, hessian=HostLagrangianHessian,
+        # the Jacobian products of the SQP call sites (reference
+        # equality_constrained_sqp.py:86,140,238): scipy's csr_matvec
+        jac_dot=lambda A, Z, x: A.dot(x), jac_tdot=lambda A, Z, y: A.T.dot(y))

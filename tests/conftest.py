@@ -18,3 +18,27 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def _device_ready():
+    """True when the CUDA library loads and a device context can be made."""
+    try:
+        from ipsolver_b200 import device
+        device.Context.default()
+        return True, ""
+    except Exception as exc:          # DeviceLibraryError: no .so or no GPU
+        return False, str(exc).splitlines()[0]
+
+
+def pytest_collection_modifyitems(config, items):
+    """``gpu`` tests are skipped (not failed) where the library or a CUDA
+    device is missing, e.g. a plain ``pytest tests`` on the build box."""
+    gpu_items = [it for it in items if "gpu" in it.keywords]
+    if not gpu_items:
+        return
+    ok, why = _device_ready()
+    if ok:
+        return
+    skip = pytest.mark.skip(reason="no usable CUDA device / library: " + why)
+    for it in gpu_items:
+        it.add_marker(skip)

@@ -42,7 +42,7 @@ def test_prototypes_cover_header():
 
 def test_info_struct_layout_matches_header():
     from ipsolver_b200 import _cabi
-    assert ctypes.sizeof(_cabi.PcgInfo) == 8 + 4 * 4 + 4 * 8 + 3 * 8
+    assert ctypes.sizeof(_cabi.PcgInfo) == 8 + 4 * 4 + 4 * 8 + 3 * 8 + 8 + 2 * 4
     assert ctypes.sizeof(_cabi.ProjInfo) == 3 * 8 + 2 * 4 + 2 * 8
 
 

@@ -416,3 +416,120 @@ def test_rank_deficient_jacobian_fails_loudly(dev):
     b = rng.standard_normal(41)                       # b[40] != b[3]: inconsistent
     with pytest.raises(dev.device.InnerSolveError):
         Y.dot(b)
+
+
+# ------------------------------------------------------------------ banded direct solve
+def _difference_matrix(m):
+    """m x (m+1) forward differences: A A' = tridiag(-1, 2, -1), whose inverse
+    does not decay at all -- the worst case for the chunked banded solve."""
+    return sps.diags([-np.ones(m), np.ones(m)], [0, 1], shape=(m, m + 1), format='csr')
+
+
+def test_band_solver_is_used_and_exact(dev):
+    """Windowed Jacobian: A A' is banded (half-bandwidth 7), the factor is
+    used, every solve takes one sweep and no refinement, and the three maps
+    agree with the oracle's SuperLU maps to 1e-12."""
+    n = 40000
+    H, A, c, b = synthetic.make_qp(n, "window", 1e4, seed=0)
+    Z, LS, Y = dev.projections(A)
+    proj = Z.projector
+    info = proj.band_info
+    if proj.params[5][0] == 1 or proj.aat_nnz < 0:
+        assert not info["in_use"]
+        pytest.skip("CG-only configuration")
+    assert info["in_use"] and info["bandwidth"] == 7 and info["trusted"]
+    Zo, LSo, Yo = oracle.build_projectors(A)
+    for op, ref, v in ((Z, Zo, c), (LS, LSo, c), (Y, Yo, b)):
+        got = op.dot(v)
+        assert proj.last_info.inner_iters == 1 and proj.last_info.n_refinements == 0
+        assert proj.last_info.n_fallbacks == 0
+        assert_close(got, ref.dot(v), 1e-12)
+    assert proj.band_info["trusted"]
+
+
+def test_band_solver_falls_back_to_cg(dev):
+    """A A' banded but with a non-decaying inverse: the chunked sweeps are not
+    accurate, the residual check notices, the solve is redone by CG and the
+    factor is switched off -- results stay right."""
+    m = 700
+    A = _difference_matrix(m)
+    rng = np.random.RandomState(1)
+    x, b = rng.standard_normal(m + 1), rng.standard_normal(m)
+    Z, LS, Y = dev.projections(A)
+    proj = Z.projector
+    Zo, LSo, Yo = oracle.build_projectors(A)
+    band_on = proj.band_info["in_use"]
+    y = Y.dot(b)
+    assert_close(y, Yo.dot(b), 1e-8)
+    if band_on:
+        assert proj.last_info.n_fallbacks >= 1
+        assert not proj.band_info["trusted"]
+    z = Z.dot(x)
+    assert_close(z, Zo.dot(x), 1e-8, floor=1e-9)
+    assert_close(LS.dot(x), LSo.dot(x), 1e-8)
+    # a refresh (new values, same pattern) gives the factor another chance
+    Z2, _, Y2 = dev.projections(sps.csr_matrix(A * 2.0))
+    assert_close(Y2.dot(b), Yo.dot(b) / 2.0, 1e-8)
+
+
+def test_band_small_dense_systems_are_direct(dev):
+    """m <= 8 rows: the band holds the whole of A A', so the sweep is a plain
+    Cholesky solve (the reference's tiny test problems)."""
+    rng = np.random.RandomState(4)
+    for m, n in ((1, 5), (2, 4), (5, 30), (8, 20)):
+        A = sps.csr_matrix(rng.standard_normal((m, n)))
+        Z, LS, Y = dev.projections(A)
+        b = rng.standard_normal(m)
+        Ad = A.toarray()
+        assert_close(Y.dot(b), Ad.T.dot(np.linalg.solve(Ad.dot(Ad.T), b)), 1e-11)
+
+
+def test_repeated_tiny_solves_are_reproducible(dev):
+    """Stress of the per-CTA reduction scratch (double-buffered by barrier
+    parity): a tiny problem leaves almost no work between a collect and the
+    next publish; 300 repetitions must give bit-identical results."""
+    H, A, c, b, kw, _ = cases.PCG_CASES["box_active_maxiter"]
+    Hs, As = sps.csc_matrix(np.array(H, float)), sps.csc_matrix(np.array(A, float))
+    Z, _, Y = dev.projections(As)
+    kw = dict(kw)
+    kw.pop("return_all", None)
+    x0, info0 = dev.qp.projected_cg(Hs, np.array(c, float), Z, Y, np.array(b, float), **kw)
+    for _ in range(300):
+        x, info = dev.qp.projected_cg(Hs, np.array(c, float), Z, Y, np.array(b, float), **kw)
+        assert np.array_equal(x, x0) and info == info0
+    lb, ub = synthetic.box_bounds(64, 0.3)
+    Hq, Aq, cq, bq = synthetic.make_qp(64, "window", 1e2, seed=0)
+    Zq, _, Yq = dev.projections(Aq)
+    d0 = dev.qp.modified_dogleg(Aq, Yq, bq, 0.5, lb, ub)
+    for _ in range(300):
+        assert np.array_equal(dev.qp.modified_dogleg(Aq, Yq, bq, 0.5, lb, ub), d0)
+
+
+def test_two_hessians_with_one_pattern_do_not_mix(dev):
+    """Operators sharing a cached device CSR re-upload their own values when
+    another operator wrote there last."""
+    n = 500
+    S1 = synthetic.banded_spd_hessian(n, 10.0, seed=1)
+    S2 = sps.csr_matrix((S1.data * 3.0 + 1.0, S1.indices, S1.indptr), shape=S1.shape)
+    v = np.random.RandomState(2).standard_normal(n)
+    H1, H2 = dev.qp.HessianOperator(n, [S1]), dev.qp.HessianOperator(n, [S2])
+    assert np.array_equal(H1.dot(v), S1.dot(v))
+    assert np.array_equal(H2.dot(v), S2.dot(v))
+    assert np.array_equal(H1.dot(v), S1.dot(v))
+    assert np.array_equal(H2.dot(v), S2.dot(v))
+
+
+def test_same_jacobian_object_is_not_uploaded_again(dev):
+    """A LinearConstraint's Jacobian comes back as the same object every outer
+    iteration: projections() then reuses the binding (no upload, no refresh);
+    an in-place edit of its values is noticed."""
+    H, A, c, b = synthetic.make_qp(3000, "window", 1e2, seed=0)
+    Z1, _, _ = dev.projections(A)
+    launches = dev.ctx.launches
+    Z2, _, _ = dev.projections(A)
+    assert Z2.binding is Z1.binding and dev.ctx.launches == launches
+    z_before = Z2.dot(c)
+    A.data *= 2.0                                   # caller breaks the contract ...
+    Z3, _, _ = dev.projections(A)
+    assert Z3.binding is not Z1.binding             # ... and is not served stale values
+    assert_close(Z3.dot(c), z_before, 1e-11)        # (Z is invariant under row scaling)
