@@ -205,6 +205,32 @@ int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b,
                         double trust_radius, const double *lb, const double *ub,
                         double *x, ipb_proj_info *info);
 
+/* One outer iteration of equality_constrained_sqp between two user callbacks
+ * (equality_constrained_sqp.py:113-140) with its vectors resident in HBM, in
+ * two calls because the host decides the tangential radius:
+ *   ipb_sqp_normal_step:     dn = modified_dogleg(A, Y, b, normal_radius,
+ *                                 box_factor*lb, box_factor*ub)          (:113)  -> dn
+ *   host:                    radius_t = sqrt(radius^2 - norm(dn)^2)      (:127)
+ *   ipb_sqp_tangential_step: c_t = H dn + c                              (:125)
+ *                            dt = projected_cg(H, c_t, Z, Y, 0, radius_t,
+ *                                              lb - dn, ub - dn)         (:128-132)
+ *                            d = dn + dt, H d, A d                       (:135-140)
+ * c / b: host vectors to upload, or NULL = unchanged since the last call on
+ * this context (they stay resident); lb / ub: NULL = unbounded, uploaded only
+ * when bounds_changed or never seen.  Vectors the device already holds (dn,
+ * c_t, the shifted bounds, d) are never uploaded again; the scalars of the
+ * iteration are left to the host on the downloaded d, H d, A d (Ad may be NULL
+ * when m = 0).  ipb_sqp_multipliers: v = -LS c, ||c + A'v||_inf (:227, :238);
+ * its c becomes the resident gradient of the following steps. */
+int ipb_sqp_normal_step(ipb_ctx *ctx, ipb_proj *P, const double *c, const double *b,
+                        double normal_radius, const double *lb, const double *ub,
+                        int bounds_changed, double box_factor, double *dn, ipb_proj_info *info);
+int ipb_sqp_tangential_step(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P,
+                            double tangential_radius, double *d, double *Hd, double *Ad,
+                            ipb_pcg_info *info);
+int ipb_sqp_multipliers(ipb_ctx *ctx, ipb_proj *P, const double *c, double *v,
+                        double *optimality, ipb_proj_info *info);
+
 /* Replaces box_sphere_intersections(z, d, lb, ub, trust_radius, entire_line)
  * (qp_subproblem.py:237-303); with lb = ub = NULL it is sphere_intersections
  * (:66-149), with trust_radius = +inf it is box_intersections (:152-234, the

@@ -98,6 +98,13 @@ struct ipb_ctx {
     std::string err;
     unsigned long long *trace = nullptr;   // barrier timeline of the next launches (ipb_trace_*)
     int trace_cap = 0;
+    // vectors of the fused SQP step (ipb_sqp_step): resident across outer iterations
+    double *step = nullptr;
+    size_t step_len = 0;
+    int64_t step_n = -1, step_m = -1;
+    bool step_has_c = false, step_has_b = false, step_has_box = false;
+    double *glue_partials = nullptr, *glue_sums = nullptr;
+    unsigned *glue_counter = nullptr;
     // ---- multi-GPU (ipb_comm_*): symmetric arena + peer mappings
     int rank = 0, size = 1;
     char *arena = nullptr;             // [mailbox | flags | seq | vectors]
@@ -367,6 +374,7 @@ extern "C" int ipb_ctx_destroy(ipb_ctx *ctx) {
     cudaFree(ctx->barrier); cudaFree(ctx->partials); cudaFree(ctx->abort_flag);
     cudaFree(ctx->d_result); cudaFreeHost(ctx->h_result);
     cudaFree(ctx->ws); cudaFree(ctx->stage); cudaFree(ctx->cub_tmp); cudaFree(ctx->trace);
+    cudaFree(ctx->step); cudaFree(ctx->glue_partials); cudaFree(ctx->glue_sums); cudaFree(ctx->glue_counter);
     for (int q = 0; q < ctx->size; ++q)
         if (q != ctx->rank && ctx->peer_base[q]) cudaIpcCloseMemHandle(ctx->peer_base[q]);
     cudaFree(ctx->arena); cudaFree(ctx->send_ent[0]); cudaFree(ctx->send_ent[1]);
@@ -1308,22 +1316,14 @@ extern "C" int ipb_projected_cg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, co
 }
 
 // ------------------------------------------------------------------ dogleg
-extern "C" int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b, double trust_radius,
-                                   const double *lb, const double *ub, double *x,
-                                   ipb_proj_info *info) {
-    if (!ctx || !P || !b || !x) return IPB_ERR_INVALID;
-    SINGLE_GPU_ONLY(ctx);
+// modified_dogleg on device vectors; the result is left in ctx->ws (returned pointer).
+static int run_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *db, double trust_radius,
+                      const double *dlb, const double *dub, const double **d_out,
+                      ipb_proj_info *info) {
     const int64_t n = P->n, m = P->m;
-    const bool box = lb && ub;
+    const bool box = dlb && dub;
     const size_t ns = vstride(n), mstr = vstride(m);
-    CHECK(ensure_stage(ctx, mstr + (box ? 2 * ns : 0)));
     CHECK(ensure_ws(ctx, 7 * ns + mstr));
-    double *db = ctx->stage, *dlb = db + mstr, *dub = dlb + (box ? ns : 0);
-    if (m) CU(ctx, cudaMemcpyAsync(db, b, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (box && n) {
-        CU(ctx, cudaMemcpyAsync(dlb, lb, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(dub, ub, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    }
     DoglegArgs a;
     memset(&a, 0, sizeof a);
     a.P = proj_view(P); a.S = sync_view(ctx);
@@ -1339,7 +1339,6 @@ extern "C" int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b, d
     CHECK(launch_coop(ctx, k_dogleg, a, proj_grid(ctx, P), &ms));
     ProjArgs::Result *h = (ProjArgs::Result *)ctx->h_result;
     CU(ctx, cudaMemcpyAsync(h, ctx->d_result, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
-    if (n) CU(ctx, cudaMemcpyAsync(x, a.out, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (info) {
         info->inner_iters = h->inner_iters; info->n_solves = h->n_solves;
@@ -1348,6 +1347,183 @@ extern "C" int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b, d
     }
     if (h->status != 0)
         IPB_FAIL(ctx, h->status, "modified dogleg: inner solve failed (status %d)", h->status);
+    *d_out = a.out;
+    return IPB_OK;
+}
+
+extern "C" int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b, double trust_radius,
+                                   const double *lb, const double *ub, double *x,
+                                   ipb_proj_info *info) {
+    if (!ctx || !P || !b || !x) return IPB_ERR_INVALID;
+    SINGLE_GPU_ONLY(ctx);
+    const int64_t n = P->n, m = P->m;
+    const bool box = lb && ub;
+    const size_t ns = vstride(n), mstr = vstride(m);
+    CHECK(ensure_stage(ctx, mstr + (box ? 2 * ns : 0)));
+    double *db = ctx->stage, *dlb = db + mstr, *dub = dlb + (box ? ns : 0);
+    if (m) CU(ctx, cudaMemcpyAsync(db, b, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (box && n) {
+        CU(ctx, cudaMemcpyAsync(dlb, lb, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(dub, ub, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const double *dout = nullptr;
+    CHECK(run_dogleg(ctx, P, db, trust_radius, box ? dlb : nullptr, box ? dub : nullptr, &dout, info));
+    if (n) CU(ctx, cudaMemcpyAsync(x, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+// ------------------------------------------------------------------ device-resident SQP step
+// One outer iteration of the Byrd-Omojokun SQP between two user callbacks
+// (reference equality_constrained_sqp.py:113-140) with its vectors resident in
+// HBM, in two calls because the host decides the tangential radius:
+//   normal:      dn = modified_dogleg(A, Y, b, zeta*radius, box*lb, box*ub)      -> dn
+//   (host)       radius_t = sqrt(radius^2 - norm(dn)^2)        (numpy, as the reference)
+//   tangential:  c_t = H dn + c;  dt = projected_cg(H, c_t, Z, Y, 0, radius_t, lb - dn, ub - dn)
+//                d = dn + dt;  H d;  A d                                         -> d, H d, A d
+// c, b and finite bounds go up only when they changed; nothing the device
+// already holds (dn, c_t, the shifted bounds, d) is uploaded again.  All SCALARS
+// of the iteration (norms, the quadratic model) are left to the host's numpy on
+// the downloaded vectors: runs that end by xtol are decided by round-off in
+// exactly these scalars, and a device reduction order would change their tail.
+static int glue(ipb_ctx *ctx, int mode, int64_t len, const double *a, const double *b,
+                const double *c, double *o0, double *o1, double s0, int slot) {
+    GlueArgs g;
+    g.mode = mode; g.len = (int)len; g.a = a; g.b = b; g.c = c; g.o0 = o0; g.o1 = o1; g.s0 = s0;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(1024, (len + 255) / 256));
+    g.partials = ctx->glue_partials; g.counter = ctx->glue_counter;
+    g.sums = ctx->glue_sums + 3 * slot;
+    k_glue<<<grid, 256, 0, ctx->stream>>>(g);
+    ctx->launches += 1;
+    return IPB_OK;
+}
+
+enum { SV_C = 0, SV_LB, SV_UB, SV_LBN, SV_UBN, SV_LBT, SV_UBT, SV_DN, SV_CT, SV_DT, SV_D, SV_HD,
+       SV_ATV, SV_NCOUNT };
+enum { SM_B = 0, SM_LIN, SM_ZERO, SM_V, SM_MCOUNT };
+
+static int ensure_step(ipb_ctx *ctx, int64_t n, int64_t m) {
+    SINGLE_GPU_ONLY(ctx);
+    if (!ctx->glue_partials) {
+        CHECK(dalloc(ctx, &ctx->glue_partials, 3 * 1024));
+        CHECK(dalloc(ctx, &ctx->glue_sums, 3 * 8));
+        CHECK(dalloc(ctx, &ctx->glue_counter, 1));
+        CU(ctx, cudaMemset(ctx->glue_counter, 0, sizeof(unsigned)));
+    }
+    if (ctx->step_n == n && ctx->step_m == m) return IPB_OK;
+    const size_t need = SV_NCOUNT * vstride(n) + SM_MCOUNT * vstride(m);
+    if (ctx->step_len < need) {
+        cudaFree(ctx->step);
+        ctx->step = nullptr; ctx->step_len = 0;
+        CHECK(dalloc(ctx, &ctx->step, need));
+        ctx->step_len = need;
+    }
+    ctx->step_n = n; ctx->step_m = m;
+    ctx->step_has_c = ctx->step_has_b = ctx->step_has_box = false;
+    double *zero = ctx->step + SV_NCOUNT * vstride(n) + SM_ZERO * vstride(m);
+    CU(ctx, cudaMemsetAsync(zero, 0, vstride(m) * 8, ctx->stream));
+    return IPB_OK;
+}
+static inline double *step_n(ipb_ctx *ctx, int k) { return ctx->step + (size_t)k * vstride(ctx->step_n); }
+static inline double *step_m(ipb_ctx *ctx, int k) {
+    return ctx->step + SV_NCOUNT * vstride(ctx->step_n) + (size_t)k * vstride(ctx->step_m);
+}
+
+extern "C" int ipb_sqp_normal_step(ipb_ctx *ctx, ipb_proj *P, const double *c, const double *b,
+                                   double normal_radius, const double *lb, const double *ub,
+                                   int bounds_changed, double box_factor, double *dn,
+                                   ipb_proj_info *info) {
+    if (!ctx || !P || !dn) return IPB_ERR_INVALID;
+    const int64_t n = P->n, m = P->m;
+    CHECK(ensure_step(ctx, n, m));
+    const bool box = lb && ub;
+    double *dc = step_n(ctx, SV_C), *db = step_m(ctx, SM_B);
+    if (c) {
+        if (n) CU(ctx, cudaMemcpyAsync(dc, c, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->step_has_c = true;
+    }
+    if (b) {
+        if (m) CU(ctx, cudaMemcpyAsync(db, b, (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->step_has_b = true;
+    }
+    if (!ctx->step_has_c || !ctx->step_has_b)
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "ipb_sqp_normal_step: c / b were never uploaded for this problem");
+    if (box && (bounds_changed || !ctx->step_has_box)) {
+        CU(ctx, cudaMemcpyAsync(step_n(ctx, SV_LB), lb, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(step_n(ctx, SV_UB), ub, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CHECK(glue(ctx, 5, n, step_n(ctx, SV_LB), step_n(ctx, SV_UB), nullptr, step_n(ctx, SV_LBN),
+                   step_n(ctx, SV_UBN), box_factor, 7));
+    }
+    ctx->step_has_box = box;
+    const double *dn_ws = nullptr;
+    CHECK(run_dogleg(ctx, P, db, normal_radius, box ? step_n(ctx, SV_LBN) : nullptr,
+                     box ? step_n(ctx, SV_UBN) : nullptr, &dn_ws, info));
+    double *ddn = step_n(ctx, SV_DN);
+    if (n) {
+        CU(ctx, cudaMemcpyAsync(ddn, dn_ws, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(dn, ddn, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+extern "C" int ipb_sqp_tangential_step(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P,
+                                       double tangential_radius, double *d, double *Hd,
+                                       double *Ad, ipb_pcg_info *info) {
+    if (!ctx || !H || !P || !d || !Hd || !info) return IPB_ERR_INVALID;
+    const int64_t n = P->n, m = P->m;
+    if (H->n != n) IPB_FAIL(ctx, IPB_ERR_INVALID, "H and A do not match");
+    if (ctx->step_n != n || ctx->step_m != m || !ctx->step_has_c)
+        IPB_FAIL(ctx, IPB_ERR_INVALID, "ipb_sqp_tangential_step needs ipb_sqp_normal_step first");
+    const bool box = ctx->step_has_box;
+    double *dc = step_n(ctx, SV_C), *dn = step_n(ctx, SV_DN);
+    // c_t = H dn + c  (:125)
+    CHECK(run_hess(ctx, H, dn, step_n(ctx, SV_HD)));
+    CHECK(glue(ctx, 0, n, step_n(ctx, SV_HD), dc, dn, step_n(ctx, SV_CT), nullptr, 0.0, 0));
+    if (box)                                                   // lb - dn, ub - dn  (:128-129)
+        CHECK(glue(ctx, 1, n, step_n(ctx, SV_LB), step_n(ctx, SV_UB), dn, step_n(ctx, SV_LBT),
+                   step_n(ctx, SV_UBT), 0.0, 7));
+    int st = run_pcg(ctx, H, P, step_n(ctx, SV_CT), step_m(ctx, SM_ZERO), tangential_radius,
+                     box ? step_n(ctx, SV_LBT) : nullptr, box ? step_n(ctx, SV_UBT) : nullptr, -1.0, -1,
+                     -1, step_n(ctx, SV_DT), nullptr, 0, info);
+    if (st != IPB_OK) { cudaStreamSynchronize(ctx->stream); return st; }
+    // d = dn + dt, H d, A d  (:135-140)
+    CHECK(glue(ctx, 2, n, dn, step_n(ctx, SV_DT), dc, step_n(ctx, SV_D), nullptr, 0.0, 1));
+    if (n) CU(ctx, cudaMemcpyAsync(d, step_n(ctx, SV_D), (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CHECK(run_hess(ctx, H, step_n(ctx, SV_D), step_n(ctx, SV_HD)));
+    if (n) CU(ctx, cudaMemcpyAsync(Hd, step_n(ctx, SV_HD), (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m > 0 && Ad) {
+        CHECK(run_matvec(ctx, csr_view(P->A), step_n(ctx, SV_D), step_m(ctx, SM_LIN)));
+        CU(ctx, cudaMemcpyAsync(Ad, step_m(ctx, SM_LIN), (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPB_OK;
+}
+
+// v = -LS c and ||c + A'v||_inf after an accepted step (reference :227, :238);
+// c becomes the resident gradient of the following ipb_sqp_step calls.
+extern "C" int ipb_sqp_multipliers(ipb_ctx *ctx, ipb_proj *P, const double *c, double *v,
+                                   double *optimality, ipb_proj_info *info) {
+    if (!ctx || !P || !c || !v || !optimality) return IPB_ERR_INVALID;
+    const int64_t n = P->n, m = P->m;
+    CHECK(ensure_step(ctx, n, m));
+    double *dc = step_n(ctx, SV_C);
+    if (n) CU(ctx, cudaMemcpyAsync(dc, c, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->step_has_c = true;
+    double *dv = step_m(ctx, SM_V), *atv = step_n(ctx, SV_ATV);
+    if (m > 0) {
+        CHECK(run_proj(ctx, P, 1, dc, step_m(ctx, SM_LIN), 0, info));
+        CHECK(glue(ctx, 6, m, step_m(ctx, SM_LIN), nullptr, nullptr, dv, nullptr, 0.0, 7));
+        CHECK(run_matvec(ctx, P->parts ? csr_view(P->pAt_raw) : csr_view_t(P->A), dv, atv));
+    } else {
+        if (n) CU(ctx, cudaMemsetAsync(atv, 0, (size_t)n * 8, ctx->stream));
+    }
+    CHECK(glue(ctx, 7, n, dc, atv, nullptr, nullptr, nullptr, 0.0, 4));
+    double opt = 0.0;
+    CU(ctx, cudaMemcpyAsync(&opt, ctx->glue_sums + 12, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (m) CU(ctx, cudaMemcpyAsync(v, dv, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *optimality = opt;
     return IPB_OK;
 }
 

@@ -552,7 +552,7 @@ __device__ __forceinline__ Epi epi_plain(double *y) {
 // addv[r] and dotv[r] are passed in (fetched together with the gathers, so
 // their latency overlaps); the rarely used operands are read here.
 __device__ __forceinline__ void row_out(const Epi &e, int r, double s, double addv_r,
-                                        double dotv_r, double &acc0, double &acc1) {
+                                        double dotv_r, double post_r, double &acc0, double &acc1) {
     double y = s;
     if (e.sa != 1.0) y = e.sa * y;
     if (e.addv) y = y + e.sb * addv_r;
@@ -560,7 +560,7 @@ __device__ __forceinline__ void row_out(const Epi &e, int r, double s, double ad
     if (e.dotv) acc0 += y * dotv_r;
     if (e.want_sq) acc1 += (e.wv ? e.wv[r] * (y * y) : y * y);
     if (e.post) {
-        const double yp = y * e.post[r];
+        const double yp = y * post_r;
         if (e.want_psq) acc0 += yp * yp;
         e.y[r] = yp;
     } else {
@@ -582,6 +582,25 @@ __device__ __forceinline__ BlockDesc load_desc(const int4 *desc, size_t blk) {
     return d;
 }
 
+// The rows are so short that a global load of an epilogue operand (addv[r] or
+// post[r]) issued inside the row loop is fully exposed.  Its slice for the
+// block's rows is therefore staged too, in whichever array of the stage has
+// room behind the block's own data: the tail of xs (blocks with a narrow
+// column span: A', M) or the tail of val (blocks with few non-zeros: A).
+constexpr int OPND_MAX = RMAX + PAD;            // doubles of an operand slice
+__device__ __forceinline__ int opnd_slot(const BlockDesc &d, bool xstage) {
+    // 1: tail of xs, 2: tail of val, 0: not staged
+    if (d.len > CHUNK) return 0;
+    if (xstage && d.xcnt <= XMAX - OPND_MAX) return 1;
+    if (((d.p0 + d.len - (d.p0 & ~3) + 3) & ~3) <= CHUNK + PAD - OPND_MAX) return 2;
+    return 0;
+}
+__device__ __forceinline__ const double *opnd_ptr(const Stage &st, int slot) {
+    return slot == 1 ? st.xs + (XMAX - OPND_MAX) : st.val + (CHUNK + PAD - OPND_MAX);
+}
+static_assert(((XMAX - OPND_MAX) * 8) % 16 == 0 && ((CHUNK + PAD - OPND_MAX) * 8) % 16 == 0 &&
+              XMAX > OPND_MAX, "operand slots must be 16-byte aligned");
+
 // The calling thread starts the bulk copies of a row block into stage ``s``: the val /
 // col / rowptr slices and, when xstage, the slice of x the block's columns
 // address -- so the block is then processed entirely out of shared memory.
@@ -591,7 +610,7 @@ __device__ __forceinline__ BlockDesc load_desc(const int4 *desc, size_t blk) {
 // so that the parity of every slot keeps advancing once per use.
 __device__ __forceinline__ void stage_issue(const CsrView &M, const BlockDesc d,
                                             const double *x, bool xstage,
-                                            Smem &sm, int s) {
+                                            Smem &sm, int s, const double *opnd = nullptr) {
     if (d.len <= CHUNK) {
         const int p0a = d.p0 & ~3, r0a = d.r0 & ~3;
         const unsigned cnt = (unsigned)((d.p0 + d.len - p0a + 3) & ~3);
@@ -603,9 +622,12 @@ __device__ __forceinline__ void stage_issue(const CsrView &M, const BlockDesc d,
         // in an earlier phase, was fenced by its writers at the grid barrier;
         // an unqualified fence here would wait for this thread's global stores.)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        unsigned tx = cnt * 12u + rcnt * 4u + xcnt * 8u;
+        const int oslot = opnd ? opnd_slot(d, xstage) : 0;
+        const unsigned ocnt = oslot ? (unsigned)((d.r1 - r0a + 3) & ~3) : 0u;
+        unsigned tx = cnt * 12u + rcnt * 4u + xcnt * 8u + ocnt * 8u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                      ::"r"(smem_addr(&sm.full[s])), "r"(tx) : "memory");
+        if (ocnt) bulk_g2s(const_cast<double *>(opnd_ptr(st, oslot)), opnd + r0a, ocnt * 8u, &sm.full[s]);
         bulk_g2s(st.val, M.val + p0a, cnt * 8u, &sm.full[s]);
         bulk_g2s(st.col, M.col + p0a, cnt * 4u, &sm.full[s]);
         bulk_g2s(st.rowptr, M.rowptr + r0a, rcnt * 4u, &sm.full[s]);
@@ -623,9 +645,12 @@ __device__ __forceinline__ void stage_issue(const CsrView &M, const BlockDesc d,
 // bit-identical to it.
 template <bool XS, bool FAST>
 __device__ __forceinline__ void block_rows(const Stage &st, const BlockDesc &d,
-                                           const double *x, const Epi &e,
-                                           double &acc0, double &acc1) {
+                                           const double *x, const Epi &e, const double *opnd,
+                                           bool xstage, double &acc0, double &acc1) {
     const int p0a = d.p0 & ~3, r0a = d.r0 & ~3;
+    // staged slice of the epilogue operand (addv, else post), indexed by global row
+    const int oslot = (!FAST && opnd) ? opnd_slot(d, xstage) : 0;
+    const double *so = oslot ? opnd_ptr(st, oslot) - r0a : nullptr;
     const double *sv = st.val - p0a;          // sv[q], q a global nnz index
     const int *sc = st.col - p0a;
     const int *rp = st.rowptr - r0a;          // rp[r], r a global row index
@@ -639,7 +664,7 @@ __device__ __forceinline__ void block_rows(const Stage &st, const BlockDesc &d,
             const unsigned off = (unsigned)(r - d.c0);
             dvv = (dot_is_x && off < (unsigned)d.xcnt) ? st.xs[off] : e.dotv[r];
         }
-        if (!FAST && e.addv) avv = e.addv[r];
+        if (!FAST && e.addv) avv = so ? so[r] : e.addv[r];
         double sum = 0.0;
         for (; q + 1 < qe; q += 2) {
             const int c0 = sc[q], c1 = sc[q + 1];
@@ -653,7 +678,8 @@ __device__ __forceinline__ void block_rows(const Stage &st, const BlockDesc &d,
             if (e.dotv) acc0 += sum * dvv;
             e.y[r] = sum;
         } else {
-            row_out(e, r, sum, avv, dvv, acc0, acc1);
+            row_out(e, r, sum, avv, dvv, (so && !e.addv) ? so[r] : (e.post ? e.post[r] : 1.0),
+                    acc0, acc1);
         }
     }
 }
@@ -681,16 +707,20 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
 #define IPB_BLK(j) (rev ? nmine - 1 - (j) : (j))
     // x slices are staged only when the bulk-copy source is 16-byte aligned
     const bool xstage = (reinterpret_cast<size_t>(x) & 15) == 0;
+    // epilogue operand staged with the blocks (never aliases y: a block's slice is
+    // read before its rows are written, by the copy this CTA waits for)
+    const double *opnd = FAST ? nullptr : (e.addv ? e.addv : e.post);
+    if (opnd && (reinterpret_cast<size_t>(opnd) & 15) != 0) opnd = nullptr;
     if (M.space == 2) {
         // measurement only: the row arithmetic without the copy pipeline -- the
         // CTA's first block is staged once and processed nmine times
         const BlockDesc d0 = load_desc(dp, 0);
         if (d0.len > CHUNK) return;
-        if (tid == 0) stage_issue(M, d0, x, xstage, sm, base % NSTAGE);
+        if (tid == 0) stage_issue(M, d0, x, xstage, sm, base % NSTAGE, opnd);
         mbar_wait(&sm.full[base % NSTAGE], (base / NSTAGE) & 1u, S.abort_flag);
         for (int j = 0; j < nmine; ++j) {
-            if (xstage && d0.xcnt > 0) block_rows<true, FAST>(sm.st[base % NSTAGE], d0, x, e, acc0, acc1);
-            else block_rows<false, FAST>(sm.st[base % NSTAGE], d0, x, e, acc0, acc1);
+            if (xstage && d0.xcnt > 0) block_rows<true, FAST>(sm.st[base % NSTAGE], d0, x, e, opnd, xstage, acc0, acc1);
+            else block_rows<false, FAST>(sm.st[base % NSTAGE], d0, x, e, opnd, xstage, acc0, acc1);
         }
         __syncthreads();
         if (tid == 0) sm.seq = base + 1u;
@@ -700,7 +730,7 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
         for (int k = 0; k < NSTAGE && k < nmine; ++k) {
             const BlockDesc dk = load_desc(dp, IPB_BLK(k));
             if (dist && dk.ghost) ghost_wait(S, sm, M.space);
-            stage_issue(M, dk, x, xstage, sm, (base + k) % NSTAGE);
+            stage_issue(M, dk, x, xstage, sm, (base + k) % NSTAGE, opnd);
         }
     BlockDesc d = load_desc(dp, IPB_BLK(0));
     for (int j = 0; j < nmine; ++j) {
@@ -711,8 +741,8 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
         if (d.len <= CHUNK) {
             mbar_wait(&sm.full[s], (u / NSTAGE) & 1u, S.abort_flag);
             if (!e.y) { /* copy pipeline only (bench) */ }
-            else if (xstage && d.xcnt > 0) block_rows<true, FAST>(sm.st[s], d, x, e, acc0, acc1);
-            else block_rows<false, FAST>(sm.st[s], d, x, e, acc0, acc1);
+            else if (xstage && d.xcnt > 0) block_rows<true, FAST>(sm.st[s], d, x, e, opnd, xstage, acc0, acc1);
+            else block_rows<false, FAST>(sm.st[s], d, x, e, opnd, xstage, acc0, acc1);
         } else {
             // one long row: the whole CTA strides over it, fixed-order tree
             double part = 0.0;
@@ -727,7 +757,7 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
 #pragma unroll
                 for (int w = 1; w < WARPS; ++w) sum += sm.red[w];
                 row_out(e, d.r0, sum, e.addv ? e.addv[d.r0] : 0.0,
-                        e.dotv ? e.dotv[d.r0] : 0.0, acc0, acc1);
+                        e.dotv ? e.dotv[d.r0] : 0.0, e.post ? e.post[d.r0] : 1.0, acc0, acc1);
             }
         }
         // hand the stage back; the last warp to do so refills it
@@ -740,7 +770,7 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
                 __threadfence_block();
                 if (j + NSTAGE < nmine) {
                     if (dist && dfar.ghost) ghost_wait(S, sm, M.space);
-                    stage_issue(M, dfar, x, xstage, sm, s);
+                    stage_issue(M, dfar, x, xstage, sm, s, opnd);
                 }
             }
         }
@@ -780,7 +810,8 @@ __device__ __noinline__ void gemv_dense(const double *D, int nx, const double *x
         for (; c < nx; c += 32) s0 += ldg_stream(row + c) * x[c];
         double s = warp_reduce((s0 + s1) + (s2 + s3), OP_SUM);
         if (lane == 0)
-            row_out(e, r, s, e.addv ? e.addv[r] : 0.0, e.dotv ? e.dotv[r] : 0.0, acc0, acc1);
+            row_out(e, r, s, e.addv ? e.addv[r] : 0.0, e.dotv ? e.dotv[r] : 0.0,
+                    e.post ? e.post[r] : 1.0, acc0, acc1);
     }
 }
 
@@ -1770,13 +1801,18 @@ k_projected_cg(const PcgArgs a) {
                     t[2 * TS + e] = t[2 * TS + e] + alpha * t[3 * TS + e];
                 });
             }
-            publish(S, sm, 0, sq, OP_SUM);
-            publish(S, sm, 1, out, OP_MAX);
-            set_ops(sm, OP_SUM, OP_MAX);
+            // ||x_next|| and the box flag decide nothing when the region is the whole
+            // space: no reduction (and, row-partitioned, no cross-GPU exchange) then
+            const bool unbounded = !a.has_box && isinf(a.radius);
+            if (!unbounded) {
+                publish(S, sm, 0, sq, OP_SUM);
+                publish(S, sm, 1, out, OP_MAX);
+                set_ops(sm, OP_SUM, OP_MAX);
+            }
             grid_sync(S, sm);
-            collect(S, sm, 2);
-            double nxn = sqrt(sm.out[0]);
-            bool inside = !(sm.out[1] > 0.0);
+            if (!unbounded) collect(S, sm, 2);
+            double nxn = unbounded ? 0.0 : sqrt(sm.out[0]);
+            bool inside = unbounded || !(sm.out[1] > 0.0);
             if (nxn >= a.radius) {                                   // :583-596
                 Interval I = box_ball(S, sm, n, x, p, alpha, a.lb, a.ub, a.has_box,
                                       a.radius, 0);
@@ -2114,6 +2150,89 @@ k_matvec(const MatvecArgs a) {
     double a0 = 0.0, a1 = 0.0;
     if (a.kind == 0) spmv(a.M, a.x, epi_plain(a.y), sm, a.S, a0, a1);
     else hess_apply(a.H, a.S, a.x, a.y, nullptr, sm, a0);
+}
+
+
+// ---------------------------------------------------------------- SQP step glue
+// Elementwise stages between the solve kernels of one SQP step (ipb_sqp_step);
+// ordinary launches.  Each stage may produce up to three sums: per-CTA
+// partials, then the last CTA to finish adds them up in CTA order -- a fixed
+// order, so the scalars are run-to-run reproducible.
+struct GlueArgs {
+    int mode, len;
+    const double *a, *b, *c;     // inputs (meaning per mode)
+    double *o0, *o1;             // outputs
+    double s0;                   // scalar parameter
+    double *partials;            // [3][gridDim.x]
+    unsigned *counter;
+    double *sums;                // [3] results
+};
+
+__global__ void __launch_bounds__(256) k_glue(const GlueArgs g) {
+    __shared__ double red[3][8];
+    __shared__ bool last;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.len; i += gridDim.x * blockDim.x) {
+        if (g.mode == 0) {                 // o0 = a + b (H dn + c); sums: ||c||^2 of input c
+            const double dn = g.c[i];
+            g.o0[i] = g.a[i] + g.b[i];
+            v0 += dn * dn;
+        } else if (g.mode == 1) {          // o0 = a - c, o1 = b - c  (lb - dn, ub - dn)
+            const double dn = g.c[i];
+            g.o0[i] = g.a[i] - dn;
+            g.o1[i] = g.b[i] - dn;
+        } else if (g.mode == 2) {          // o0 = d = a + b (dn + dt); sums: ||dt||^2, ||d||^2, c.d
+            const double dt = g.b[i], d = g.a[i] + dt;
+            g.o0[i] = d;
+            v0 += dt * dt; v1 += d * d; v2 += g.c[i] * d;
+        } else if (g.mode == 3) {          // sums: a.b (Hd.d)
+            v0 += g.a[i] * g.b[i];
+        } else if (g.mode == 4) {          // o0 = a + b (A d + b); sums: ||o0||^2, ||b||^2
+            const double bb = g.b[i], l = g.a[i] + bb;
+            g.o0[i] = l;
+            v0 += l * l; v1 += bb * bb;
+        } else if (g.mode == 5) {          // o0 = s0 * a, o1 = s0 * b  (scaled bounds)
+            g.o0[i] = g.s0 * g.a[i];
+            g.o1[i] = g.s0 * g.b[i];
+        } else if (g.mode == 6) {          // o0 = -a (v = -LS c)
+            g.o0[i] = -g.a[i];
+        } else if (g.mode == 7) {          // max |a + b|  (||c + A'v||_inf) in sums[0]
+            v0 = fmax(v0, fabs(g.a[i] + g.b[i]));
+        }
+    }
+    const bool is_max = g.mode == 7;
+    double v[3] = {v0, v1, v2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, v[k], o);
+            v[k] = is_max ? fmax(v[k], t) : v[k] + t;
+        }
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 3; ++k) {
+            double a = red[k][0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) a = is_max ? fmax(a, red[k][w]) : a + red[k][w];
+            g.partials[k * gridDim.x + blockIdx.x] = a;
+        }
+        __threadfence();
+        last = atomicAdd(g.counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 3) {
+        __threadfence();
+        const int k = threadIdx.x;
+        double a = is_max ? 0.0 : 0.0;
+        for (unsigned q = 0; q < gridDim.x; ++q) {
+            const double t = __ldcg(&g.partials[k * gridDim.x + q]);
+            a = is_max ? fmax(a, t) : a + t;
+        }
+        g.sums[k] = a;
+        if (k == 0) *g.counter = 0u;
+    }
 }
 
 // ---------------------------------------------------------------- setup kernels

@@ -95,6 +95,11 @@ PROTOTYPES = {
                                        C.POINTER(PcgInfo)]),
     "ipb_modified_dogleg": (C.c_int, [_P, _P, _D, C.c_double, _D, _D, _D,
                                       C.POINTER(ProjInfo)]),
+    "ipb_sqp_normal_step": (C.c_int, [_P, _P, _D, _D, C.c_double, _D, _D, C.c_int, C.c_double,
+                                      _D, C.POINTER(ProjInfo)]),
+    "ipb_sqp_tangential_step": (C.c_int, [_P, _P, _P, C.c_double, _D, _D, _D,
+                                          C.POINTER(PcgInfo)]),
+    "ipb_sqp_multipliers": (C.c_int, [_P, _P, _D, _D, _D, C.POINTER(ProjInfo)]),
     "ipb_box_sphere_intersections": (C.c_int, [_P, _I64, _D, _D, _D, _D,
                                                C.c_double, C.c_int, _D, _D,
                                                C.POINTER(C.c_int)]),

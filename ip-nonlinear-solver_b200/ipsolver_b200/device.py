@@ -353,6 +353,52 @@ class DeviceProjector:
         self._note(info)
         return x
 
+    def sqp_normal_step(self, c, b, normal_radius, lb=None, ub=None, bounds_changed=True,
+                        box_factor=0.5):
+        """``dn = modified_dogleg(...)`` with ``c`` / ``b`` / bounds kept resident
+        for :meth:`sqp_tangential_step` (``None``: unchanged since the last call)."""
+        c = None if c is None else f64(c, self.n)
+        b = None if b is None else f64(b, self.m)
+        lb, ub = _bounds(lb, ub, self.n)
+        dn = self.ctx.empty(self.n)
+        info = ProjInfo()
+        self.ctx.check(self.ctx.lib.ipb_sqp_normal_step(
+            self.ctx.h, self.h, dptr(c), dptr(b), float(normal_radius), dptr(lb), dptr(ub),
+            int(bool(bounds_changed)), float(box_factor), dptr(dn), C.byref(info)))
+        self._note(info)
+        return dn
+
+    def sqp_tangential_step(self, H, tangential_radius):
+        """``d = dn + projected_cg(H, H dn + c, ..., radius_t, lb - dn, ub - dn)``
+        on the vectors the normal step left in HBM; returns ``d, H d, A d, info``."""
+        d, Hd = self.ctx.empty(self.n), self.ctx.empty(self.n)
+        Ad = self.ctx.empty(self.m)
+        info = PcgInfo()
+        st = self.ctx.lib.ipb_sqp_tangential_step(
+            self.ctx.h, H.h, self.h, float(tangential_radius), dptr(d), dptr(Hd),
+            dptr(Ad) if self.m else None, C.byref(info))
+        self.last_pcg_info = info
+        self.ctx.check(st)
+        self.totals["inner_iters"] += info.inner_iters
+        self.totals["n_solves"] += info.n_solves
+        self.totals["n_refinements"] += info.n_refinements
+        out = {'niter': int(info.niter), 'stop_cond': int(info.stop_cond),
+               'hits_boundary': bool(info.hits_boundary)}
+        return d, Hd, Ad, out
+
+    def sqp_multipliers(self, c):
+        """``v = -LS c`` and ``||c + A'v||_inf``; ``c`` stays resident for the
+        following :meth:`sqp_step` calls."""
+        c = f64(c, self.n)
+        v = self.ctx.empty(self.m)
+        opt = C.c_double()
+        info = ProjInfo()
+        self.ctx.check(self.ctx.lib.ipb_sqp_multipliers(
+            self.ctx.h, self.h, dptr(c), dptr(v), C.byref(opt), C.byref(info)))
+        if self.m:
+            self._note(info)
+        return v, opt.value
+
     def projected_cg(self, H, c, b, trust_radius=np.inf, lb=None, ub=None,
                      tol=None, max_iter=None, max_infeasible_iter=None,
                      return_all=False):

@@ -45,10 +45,25 @@ def device_hot_path():
     def jac_tdot(A, Z, y):
         return Z.projector.A.rmatvec(y) if A.shape[0] else np.zeros(A.shape[1])
 
+    def fused_step(H, Z, c, b, radius, lb, ub, bounds_changed):
+        """Normal + tangential step on device-resident vectors:
+        ``c`` / ``b`` None = unchanged since the last call.  The host only sees
+        ``dn`` (to set the tangential radius exactly as the reference does,
+        :127) and ``d, H d, A d`` (for the scalars of :138-140)."""
+        proj = Z.projector
+        dn = proj.sqp_normal_step(c, b, ZETA_NORMAL * radius, lb, ub, bounds_changed, BOX_NORMAL)
+        radius_t = np.sqrt(radius**2 - np.linalg.norm(dn)**2)
+        d, Hd, Ad, cg_info = proj.sqp_tangential_step(_q.as_device_hessian(H, proj.n), radius_t)
+        return dn, d, Hd, Ad, cg_info
+
+    def fused_multipliers(Z, c):
+        return Z.projector.sqp_multipliers(c)
+
     return SimpleNamespace(projections=_p.projections, projected_cg=_q.projected_cg,
                            modified_dogleg=_q.modified_dogleg,
                            box_intersections=_q.box_intersections,
-                           hessian=_q.HessianOperator, jac_dot=jac_dot, jac_tdot=jac_tdot)
+                           hessian=_q.HessianOperator, jac_dot=jac_dot, jac_tdot=jac_tdot,
+                           fused_step=fused_step, fused_multipliers=fused_multipliers)
 
 
 def _identity_scaling(x):
@@ -72,9 +87,10 @@ def _next_radius(radius, ratio, step_norm):
     return radius
 
 
-def _record(state, x, v, f, c, b, A, hp, Z):
+def _record(state, x, v, f, c, b, A, hp, Z, optimality=None):
     state.x, state.v, state.fun, state.grad, state.constr, state.jac = x, v, f, c, b, A
-    state.optimality = norm(c + hp.jac_tdot(A, Z, v), np.inf)
+    state.optimality = (norm(c + hp.jac_tdot(A, Z, v), np.inf) if optimality is None
+                        else optimality)
     state.constr_violation = norm(b, np.inf) if len(b) > 0 else 0
 
 
@@ -95,8 +111,18 @@ def equality_constrained_sqp(fun_and_constr, grad_and_jac, lagr_hess,
     f, c, b, A = fun0, grad0, constr0, jac0
     S = scaling(x)
     Z, LS, Y = hp.projections(A, factorization_method)      # :81
-    v = -LS.dot(c)                                           # least-squares multipliers :83
-    _record(state, x, v, f, c, b, A, hp, Z)
+    # device hot path with matrix Hessians: the vectors of an iteration stay in HBM
+    # (one upload of c per accepted step, one download of d per iteration)
+    fused = hasattr(hp, "fused_step")
+    c_up = b_up = bounds_up = True           # what the device copy still lacks
+    bounded = bool(np.isfinite(lb).any() or np.isfinite(ub).any())
+    if fused:
+        v, opt0 = hp.fused_multipliers(Z, c)
+        c_up = False
+        _record(state, x, v, f, c, b, A, hp, Z, opt0)
+    else:
+        v = -LS.dot(c)                                       # least-squares multipliers :83
+        _record(state, x, v, f, c, b, A, hp, Z)
     state.niter += 1
     state.trust_radius, state.penalty = radius, penalty
     if return_all:
@@ -108,17 +134,29 @@ def equality_constrained_sqp(fun_and_constr, grad_and_jac, lagr_hess,
         if need_hessian:
             H = lagr_hess(x, v)
             state.nhev += 1
-        # normal step: reduce ||A d + b|| inside a shrunken region (:113)
-        dn = hp.modified_dogleg(A, Y, b, ZETA_NORMAL * radius, BOX_NORMAL * lb, BOX_NORMAL * ub)
-        # tangential step: trust-region EQP in the null space of A (:125-132)
-        c_t = H.dot(dn) + c
-        radius_t = np.sqrt(radius**2 - np.linalg.norm(dn)**2)
-        dt, cg_info = hp.projected_cg(H, c_t, Z, Y, np.zeros_like(b), radius_t, lb - dn, ub - dn)
-        d = dn + dt
-        # model and linearised constraint at the step (:138-140)
-        q_model = 1 / 2 * (H.dot(d)).dot(d) + c.T.dot(d)
-        lin_constr = hp.jac_dot(A, Z, d) + b
-        vpred = max(1e-16, norm(b) - norm(lin_constr))       # (3.52), kept positive
+        use_fused = fused and getattr(H, "device", None) is not None
+        if use_fused:
+            dn, d, Hd, Ad, cg_info = hp.fused_step(H, Z, c if c_up else None, b if b_up else None,
+                                                   radius, lb if bounded else None,
+                                                   ub if bounded else None, bounds_up)
+            c_up = b_up = bounds_up = False
+            dt = d - dn
+            norm_dn, norm_dt, norm_d = norm(dn), norm(dt), norm(d)
+            q_model = 1 / 2 * Hd.dot(d) + c.T.dot(d)
+            norm_lin = norm(Ad + b)
+        else:
+            # normal step: reduce ||A d + b|| inside a shrunken region (:113)
+            dn = hp.modified_dogleg(A, Y, b, ZETA_NORMAL * radius, BOX_NORMAL * lb, BOX_NORMAL * ub)
+            # tangential step: trust-region EQP in the null space of A (:125-132)
+            c_t = H.dot(dn) + c
+            radius_t = np.sqrt(radius**2 - np.linalg.norm(dn)**2)
+            dt, cg_info = hp.projected_cg(H, c_t, Z, Y, np.zeros_like(b), radius_t, lb - dn, ub - dn)
+            d = dn + dt
+            norm_dn, norm_dt, norm_d = norm(dn), norm(dt), norm(d)
+            # model and linearised constraint at the step (:138-140)
+            q_model = 1 / 2 * (H.dot(d)).dot(d) + c.T.dot(d)
+            norm_lin = norm(hp.jac_dot(A, Z, d) + b)
+        vpred = max(1e-16, norm(b) - norm_lin)               # (3.52), kept positive
         penalty_before = penalty
         if q_model > 0:
             penalty = max(penalty, q_model / ((1 - RHO_PENALTY) * vpred))
@@ -131,7 +169,7 @@ def equality_constrained_sqp(fun_and_constr, grad_and_jac, lagr_hess,
         state.ncev += 1
         ratio = (merit - (f_trial + penalty * norm(b_trial))) / predicted
         # second-order correction (:172-193)
-        if ratio < ETA_ACCEPT and norm(dn) <= SOC_RATIO * norm(dt):
+        if ratio < ETA_ACCEPT and norm_dn <= SOC_RATIO * norm_dt:
             y = -Y.dot(b_trial)
             _, t, hit = hp.box_intersections(d, y, lb, ub)
             x_soc = x + S.dot(d + t * y)
@@ -141,7 +179,7 @@ def equality_constrained_sqp(fun_and_constr, grad_and_jac, lagr_hess,
             ratio_soc = (merit - (f_soc + penalty * norm(b_soc))) / predicted
             if hit and ratio_soc >= ETA_ACCEPT:
                 x_trial, f_trial, b_trial, ratio = x_soc, f_soc, b_soc, ratio_soc
-        radius = _next_radius(radius, ratio, norm(d))
+        radius = _next_radius(radius, ratio, norm_d)
         state.niter += 1
         if ratio >= ETA_ACCEPT:                              # accept (:216-238)
             x, f, b = x_trial, f_trial, b_trial
@@ -150,9 +188,15 @@ def equality_constrained_sqp(fun_and_constr, grad_and_jac, lagr_hess,
             state.ngev += 1
             state.njev += 1
             Z, LS, Y = hp.projections(A)                     # method dropped here, as in :225
-            v = -LS.dot(c)
+            b_up = True
+            if fused:
+                v, opt_new = hp.fused_multipliers(Z, c)
+                c_up = False
+                _record(state, x, v, f, c, b, A, hp, Z, opt_new)
+            else:
+                v = -LS.dot(c)
+                _record(state, x, v, f, c, b, A, hp, Z)
             need_hessian = True
-            _record(state, x, v, f, c, b, A, hp, Z)
         else:                                                # reject (:240-242)
             penalty = penalty_before
             need_hessian = False

@@ -15,7 +15,7 @@ from scipy.sparse.linalg import LinearOperator
 
 from .device import Context, DeviceCSR, DeviceHessian
 from ._cabi import dptr, f64
-from .projections import DeviceMap
+from .projections import DeviceMap, _fingerprint
 
 __all__ = [
     'sphere_intersections', 'box_intersections', 'box_sphere_intersections',
@@ -87,17 +87,24 @@ class HessianOperator(LinearOperator):
             csr = None
             if self.sparse is not None:
                 S = self.sparse
-                if not S.has_canonical_format:
-                    S = S.copy()
-                    S.sum_duplicates()
-                    self.sparse = S
                 cache = ctx.__dict__.setdefault("_hess_csr_cache", {})
                 key = (S.shape, S.nnz)
                 csr = cache.pop(key, None)
-                if csr is not None and csr.same_pattern(S):
-                    csr.update_values(S.data)
+                fp = _fingerprint(S)
+                if csr is not None and getattr(csr, "host_arrays", None) is not None \
+                        and csr.host_arrays[0] is S.data and csr.host_arrays[1] is S.indices \
+                        and csr.host_arrays[2] is S.indptr and csr.host_fp == fp:
+                    pass        # the very same arrays as last time (a constant Hessian): nothing to do
                 else:
-                    csr = DeviceCSR(ctx, S, with_transpose=False)
+                    if not S.has_canonical_format:
+                        S = S.copy()
+                        S.sum_duplicates()
+                        self.sparse = S
+                    if csr is not None and csr.same_pattern(S):
+                        csr.update_values(S.data)
+                    else:
+                        csr = DeviceCSR(ctx, S, with_transpose=False)
+                    csr.host_arrays, csr.host_fp = (S.data, S.indices, S.indptr), _fingerprint(S)
                 cache[key] = csr                               # most recently used last
                 while len(cache) > 4:
                     cache.pop(next(iter(cache)))
@@ -107,6 +114,8 @@ class HessianOperator(LinearOperator):
                                       dense=self.dense, diag_tail=self.diag_tail)
         elif self._csr is not None and self._csr.last_writer is not self._token:
             self._csr.update_values(self.sparse.data)
+            self._csr.host_arrays = (self.sparse.data, self.sparse.indices, self.sparse.indptr)
+            self._csr.host_fp = _fingerprint(self.sparse)
             self._csr.last_writer = self._token
         return self._dev
 

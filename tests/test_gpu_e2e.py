@@ -97,3 +97,32 @@ def test_small_classics(api, gold, name):
     assert np.linalg.norm(res.x - gold[name + "/x"]) <= 1e-7 * max(1.0, np.linalg.norm(gold[name + "/x"]))
     assert res.fun == pytest.approx(fval, rel=1e-8, abs=1e-12)
     assert res.optimality < 1e-8 and res.constr_violation < 1e-8
+
+
+def test_fused_step_equals_the_call_by_call_loop(api):
+    """The device-resident outer step (one upload of c per accepted step, one
+    download of d per iteration) takes the same path as the loop that calls
+    modified_dogleg / projected_cg / the products one by one with host vectors."""
+    import ipsolver_b200 as ipb
+    from ipsolver_b200.equality_constrained_sqp import device_hot_path
+    from ipsolver_b200 import synthetic
+    n = 20000
+    H, A, q, b = synthetic.make_qp(n, "window", 10.0, seed=0)
+    args = (lambda x: 0.5 * x.dot(H.dot(x)) + q.dot(x), np.zeros(n), lambda x: H.dot(x) + q,
+            lambda x: H, ipb.LinearConstraint(A, ("equals", b)))
+    res_f = ipb.minimize_constrained(*args, method='equality_constrained_sqp')
+    hp = device_hot_path()
+    del hp.fused_step, hp.fused_multipliers
+    res_u = ipb.minimize_constrained(*args, method='equality_constrained_sqp', hot_path=hp)
+    assert (res_f.niter, res_f.cg_niter, res_f.nfev, res_f.status) == \
+        (res_u.niter, res_u.cg_niter, res_u.nfev, res_u.status)
+    assert rel(res_f.x, res_u.x) < 1e-10 and rel(res_f.v, res_u.v) < 1e-10
+    assert res_f.fun == pytest.approx(res_u.fun, rel=1e-13)
+    # ... and with bounds on the step (barrier subproblem: slack bounds, diagonal tail)
+    res_ip = e2e_problems.PROBLEMS["ipqp_window_1000"](api)()
+    hp_api = dict(api)
+    hp_api["minimize_constrained"] = lambda *a, **k: ipb.minimize_constrained(*a, hot_path=hp, **k)
+    res_ip_u = e2e_problems.PROBLEMS["ipqp_window_1000"](hp_api)()
+    assert abs(res_ip.niter - res_ip_u.niter) <= 0.1 * res_ip_u.niter
+    assert res_ip.fun == pytest.approx(res_ip_u.fun, rel=1e-8)
+    assert rel(res_ip.x, res_ip_u.x) < 1e-6
