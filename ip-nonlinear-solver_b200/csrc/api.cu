@@ -58,7 +58,7 @@ struct ipb_proj {
     double orth_tol = 1e-12, rtol = 1e-13;
     int max_refin = 3, maxit = 1000;
     double *v = nullptr, *r = nullptr, *w = nullptr, *p = nullptr, *s = nullptr,
-           *rhs = nullptr, *t = nullptr;
+           *rhs = nullptr, *t = nullptr, *q = nullptr;
     // explicit M = A~ A~' (pattern built once, values per refresh)
     int aat_mode = 0;                  // 0 auto, 1 never, 2 always
     bool has_M = false;
@@ -1005,6 +1005,7 @@ static int proj_vectors(ipb_ctx *ctx, ipb_proj *p) {
     CHECK(valloc(ctx, &p->v, p->m)); CHECK(valloc(ctx, &p->r, p->m));
     CHECK(valloc(ctx, &p->w, p->m)); CHECK(valloc(ctx, &p->p, p->m));
     CHECK(valloc(ctx, &p->s, p->m)); CHECK(valloc(ctx, &p->rhs, p->m));
+    CHECK(valloc(ctx, &p->q, p->m));
     CHECK(valloc(ctx, &p->t, p->n));
     return IPB_OK;
 }
@@ -1058,7 +1059,7 @@ extern "C" int ipb_proj_destroy(ipb_ctx *ctx, ipb_proj *p) {
     if (!p) return IPB_OK;
     cudaFree(p->nval); cudaFree(p->nt_val); cudaFree(p->dscale); cudaFree(p->dnorm2);
     vfree(ctx, p->v); vfree(ctx, p->r); vfree(ctx, p->w); vfree(ctx, p->p); vfree(ctx, p->s);
-    vfree(ctx, p->rhs); vfree(ctx, p->t);
+    vfree(ctx, p->rhs); vfree(ctx, p->t); vfree(ctx, p->q);
     free_aat(p);
     free_band(p);
     delete p;
@@ -1073,6 +1074,7 @@ static ProjView proj_view(const ipb_proj *p) {
     v.fro = p->fro; v.orth_tol = p->orth_tol; v.max_refin = p->max_refin;
     v.rtol = p->rtol; v.maxit = p->maxit;
     v.v = p->v; v.r = p->r; v.w = p->w; v.p = p->p; v.s = p->s; v.rhs = p->rhs; v.t = p->t;
+    v.q = p->q;
     if (p->band) {
         v.band.enabled = 1; v.band.B = p->band_B; v.band.ov = p->band_ov;
         v.band.steps = p->band_steps; v.band.ngroup = p->band_ngroup;

@@ -162,6 +162,7 @@ struct ProjView {
     int maxit;
     // work vectors
     double *v, *r, *w, *p, *s, *rhs;   // m
+    double *q;                          // m: intermediate of the squared operator (singular A A')
     double *t;                          // n
 };
 
@@ -171,13 +172,14 @@ struct ProjStats {
     double orth, max_orth;
     int band_ok;                  // banded direct solve usable (same value in every CTA)
     long long n_sweeps, n_fallbacks;
+    long long n_singular;         // solves redone as least-squares problems (singular A A')
 };
 
 __device__ __forceinline__ ProjStats proj_stats_init(const ProjView &P) {
     ProjStats st;
     st.inner_iters = st.n_solves = st.n_refinements = 0;
     st.status = 0; st.orth = st.max_orth = 0.0;
-    st.n_sweeps = st.n_fallbacks = 0;
+    st.n_sweeps = st.n_fallbacks = st.n_singular = 0;
     // read before any CTA of this launch can have cleared it (the first write
     // is behind at least one grid barrier)
     st.band_ok = (P.band.enabled && P.m > 0) ? *reinterpret_cast<volatile int *>(P.band.ok) : 0;
@@ -1202,21 +1204,38 @@ __device__ __noinline__ double band_sweep(const ProjView &P, const SyncView &S, 
 #undef IPB_BWD_STEP
 
 // ---------------------------------------------------------------- (A A')^-1
-// w = (A~ A~') r with  acc0 += w.r : one SpMV with the explicit product M
-// when the projector holds it (half the matrix bytes and no n-vector
-// round trip), otherwise A~ (A~' r) through P.t with a barrier in between.
-__device__ __forceinline__ void normal_apply(const ProjView &P, const SyncView &S,
-                                             Smem &sm, double &acc0) {
+// out = (A~ A~') in with  acc0 += out.dotv : one SpMV with the explicit
+// product M when the projector holds it (half the matrix bytes and no
+// n-vector round trip), otherwise A~ (A~' in) through P.t with a barrier in
+// between.
+__device__ __forceinline__ void normal_apply_to(const ProjView &P, const SyncView &S, Smem &sm,
+                                                const double *in, double *out,
+                                                const double *dotv, double &acc0) {
     double dummy = 0.0;
-    Epi e = epi_plain(P.w);
-    e.dotv = P.r;
+    Epi e = epi_plain(out);
+    e.dotv = dotv;
     if (P.has_M) {
-        spmv(P.M, P.r, e, sm, S, acc0, dummy);
+        spmv(P.M, in, e, sm, S, acc0, dummy);
     } else {
-        spmv(P.At, P.r, epi_plain(P.t), sm, S, acc0, dummy);
+        spmv(P.At, in, epi_plain(P.t), sm, S, acc0, dummy);
         grid_sync(S, sm);
         acc0 = 0.0;
         spmv(P.A, P.t, e, sm, S, acc0, dummy);
+    }
+}
+
+// w = K r with acc0 += w.r, K = A~ A~' -- or K = (A~ A~')^2 when ``squared``
+// (the normal equations of a singular system, see inner_solve).
+__device__ __forceinline__ void normal_apply(const ProjView &P, const SyncView &S,
+                                             Smem &sm, double &acc0, bool squared = false) {
+    if (!squared) {
+        normal_apply_to(P, S, sm, P.r, P.w, P.r, acc0);
+    } else {
+        double dummy = 0.0;
+        normal_apply_to(P, S, sm, P.r, P.q, nullptr, dummy);
+        grid_sync(S, sm);
+        acc0 = 0.0;
+        normal_apply_to(P, S, sm, P.q, P.w, P.r, acc0);
     }
 }
 
@@ -1281,20 +1300,32 @@ __device__ __noinline__ bool inner_solve_band(const ProjView &P, const SyncView 
 // is round-off noise (the second projection g = Z r of qp_subproblem.py:504)
 // is solved like any other, as the reference's factorisation does.
 __device__ __noinline__ int inner_solve_cg(const ProjView &P, const SyncView &S,
-                                           Smem &sm, ProjStats &st, int fixed_iters = 0) {
+                                           Smem &sm, ProjStats &st, int fixed_iters = 0,
+                                           bool squared = false) {
     const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
     const int m = P.m;
     double a0;
+    const double *rhs = P.rhs;
+    if (squared) {
+        // K v = M rhs with K = M^2: consistent whatever rhs is; from v = 0 CG
+        // converges to the minimum-norm least-squares solution M^+ rhs
+        double dummy = 0.0;
+        normal_apply_to(P, S, sm, P.rhs, P.q, nullptr, dummy);
+        grid_sync(S, sm);
+        for (int i = gt; i < m; i += nt) P.w[i] = P.q[i];
+        grid_sync(S, sm);
+        rhs = P.w;                      // copied to r below before w is overwritten
+    }
     // r = rhs, v = p = s = 0
     double gpart = 0.0;
     for (int i = gt; i < m; i += nt) {
-        double ri = P.rhs[i];
+        double ri = rhs[i];
         P.r[i] = ri; P.v[i] = 0.0; P.p[i] = 0.0; P.s[i] = 0.0;
         gpart += ri * ri;
     }
     grid_sync(S, sm);
     a0 = 0.0;
-    normal_apply(P, S, sm, a0);
+    normal_apply(P, S, sm, a0, squared);
     publish(S, sm, 0, a0, OP_SUM);
     publish(S, sm, 1, gpart, OP_SUM);
     set_ops(sm, OP_SUM, OP_SUM);
@@ -1314,7 +1345,7 @@ __device__ __noinline__ int inner_solve_cg(const ProjView &P, const SyncView &S,
         gpart = cg_update(P, sm, S, alpha, beta);
         grid_sync(S, sm);
         a0 = 0.0;
-        normal_apply(P, S, sm, a0);
+        normal_apply(P, S, sm, a0, squared);
         publish(S, sm, 0, a0, OP_SUM);
         publish(S, sm, 1, gpart, OP_SUM);
         grid_sync(S, sm);
@@ -1339,11 +1370,23 @@ __device__ __noinline__ int inner_solve_cg(const ProjView &P, const SyncView &S,
     return k;
 }
 
+// (A~ A~')^-1 rhs: banded direct solve, else CG; and when the CG breaks down
+// or does not converge -- A A' singular: rank-deficient Jacobian -- the
+// minimum-norm least-squares solution by CG on the squared operator, which is
+// what the reference's fallback computes (dense SVD pseudo-inverse when its
+// factorisation is singular, projections.py:101-108).  Fails loudly (status 5)
+// only if that does not converge either.
 __device__ __forceinline__ void inner_solve(const ProjView &P, const SyncView &S,
                                             Smem &sm, ProjStats &st, int fixed_iters = 0) {
     st.n_solves += 1;
     if (st.band_ok && fixed_iters <= 0 && inner_solve_band(P, S, sm, st)) return;
     inner_solve_cg(P, S, sm, st, fixed_iters);
+    if (st.status == 5 && fixed_iters <= 0 && P.q != nullptr) {
+        st.status = 0;
+        st.n_singular += 1;
+        grid_sync(S, sm);
+        inner_solve_cg(P, S, sm, st, 0, true);
+    }
 }
 
 // Z with the banded factor: the solve is checked by the product the

@@ -10,10 +10,11 @@ three constraint containers with the ``kind`` vocabulary (``("equals", c)``,
 ``("less", ub)``, ``("greater", lb)``, ``("interval", lb, ub)``), the split into
 ``c_ineq(x) <= 0`` / ``c_eq(x) = 0`` in the reference's row order (lower-bound
 rows, then upper-bound rows, per constraint; ``_canonical_constraint.py:283-360``)
-and the stopping rules (``_minimize_constrained.py:460-502``).  Finite-difference
-Hessians (``hess='2-point'`` ...) are host callbacks and are not supported:
-``hess`` must return a scipy sparse matrix or an ndarray, so that the
-Lagrangian Hessian can be applied on the device.
+and the stopping rules (``_minimize_constrained.py:460-502``).  ``hess`` returns a
+scipy sparse matrix or an ndarray (the Lagrangian Hessian is then applied on the
+device) or a ``LinearOperator`` (an opaque host callback: the CG recurrence is
+then driven from the host, projections stay on the device); the reference's
+finite-difference modes (``hess='2-point'`` ..., ``_numdiff.py``) are not built.
 """
 import time
 import warnings
@@ -275,12 +276,17 @@ def minimize_constrained(fun, x0, grad, hess, constraints=(), method=None, xtol=
 
     def lagr_hess(x, v_eq=np.empty(0), v_ineq=np.empty(0)):
         H0 = hess(x)
-        if isinstance(H0, LinearOperator):
-            raise TypeError("`hess` returned a LinearOperator: the device path needs the Hessian "
-                            "as a scipy sparse matrix or an ndarray (opaque operators are host "
-                            "callbacks; keep the reference's scipy path for them).")
+        terms = canon.hess_terms(x, v_eq, v_ineq)
+        if isinstance(H0, LinearOperator) or any(isinstance(t, LinearOperator) for t in terms):
+            # an opaque term (reference _canonical_constraint.py:131-135): the sum is a
+            # host callback; projected_cg then drives its loop from the host and only
+            # the projections run on the device
+            parts = [H0] + terms
+            return LinearOperator((len(x), len(x)), dtype=np.float64,
+                                  matvec=lambda p: sum(np.asarray(t.dot(p)).reshape(-1)
+                                                       for t in parts))
         H0 = sps.csr_matrix(H0) if sps.issparse(H0) else np.atleast_2d(np.asarray(H0))
-        return hp.hessian(len(x), [H0] + canon.hess_terms(x, v_eq, v_ineq))
+        return hp.hessian(len(x), [H0] + terms)
 
     state = OptimizeResult(niter=0, nfev=1, ngev=1, ncev=1, njev=1, nhev=0, cg_niter=0, cg_info={})
     options = dict(options)

@@ -124,18 +124,19 @@ class HessianOperator(LinearOperator):
 
 
 def as_device_hessian(H, n):
-    """Device Hessian for anything with an explicit matrix form."""
+    """Device Hessian for anything with an explicit matrix form, else None
+    (an opaque operator: ``projected_cg`` then runs its loop on the host with
+    the device projectors)."""
     if isinstance(H, HessianOperator):
         return H.device
     if isinstance(H, DeviceHessian):
         return H
     if sps.issparse(H) or isinstance(H, np.ndarray):
         return HessianOperator(n, [H]).device
-    raise TypeError(
-        "projected_cg needs H with explicit terms (HessianOperator, scipy "
-        "sparse matrix or ndarray) to run on the device; got %s. Opaque "
-        "LinearOperators (finite-difference Hessians) are host callbacks and "
-        "are outside this path." % type(H).__name__)
+    if isinstance(H, LinearOperator) or callable(getattr(H, "dot", None)):
+        return None
+    raise TypeError("projected_cg: H must be a matrix or a LinearOperator, got %s"
+                    % type(H).__name__)
 
 
 # ------------------------------------------------------------------ intersections
@@ -218,5 +219,93 @@ def projected_cg(H, c, Z, Y, b, trust_radius=np.inf, lb=None, ub=None,
     proj = _projector_of(Z, Y)
     c = np.asarray(c, dtype=np.float64)
     Hd = as_device_hessian(H, c.shape[0])
+    if Hd is None:
+        return _projected_cg_opaque(H, c, Z, Y, np.asarray(b, dtype=np.float64), trust_radius,
+                                    lb, ub, tol, max_iter, max_infeasible_iter, return_all)
     return proj.projected_cg(Hd, c, b, trust_radius, lb, ub, tol, max_iter,
                              max_infeasible_iter, return_all)
+
+
+def _projected_cg_opaque(H, c, Z, Y, b, trust_radius, lb, ub, tol, max_iter,
+                         max_infeasible_iter, return_all):
+    """``projected_cg`` for a Hessian that is only a callback (a user
+    ``LinearOperator``, a finite-difference Hessian -- reference
+    ``_minimize_constrained.py:404-406,417-419``): ``H.dot`` has to run on the
+    host, so the CG-Steihaug recurrence (Gould, Hribar & Nocedal 2001, Alg. 6.2,
+    with the sphere / box truncation of reference ``qp_subproblem.py:416-643``)
+    is driven from here, one iteration per ``H.dot``, while every projection
+    ``Z.dot`` / ``Y.dot`` (the inner solves with A A') and every intersection
+    still runs on the device."""
+    n, m = c.shape[0], b.shape[0]
+    lb = np.full(n, -np.inf) if lb is None else np.asarray(lb, dtype=np.float64)
+    ub = np.full(n, np.inf) if ub is None else np.asarray(ub, dtype=np.float64)
+    x = Y.dot(-b)
+    r = Z.dot(H.dot(x) + c)
+    g = Z.dot(r)
+    p = -g
+    trail = [x] if return_all else None
+    Hp = H.dot(p)
+    gg = np.linalg.norm(g) ** 2
+    slack = trust_radius - np.linalg.norm(x)
+    if slack < -8.0 * np.finfo(float).eps * trust_radius:
+        raise ValueError("Trust region problem does not have a solution.")
+    info = {'niter': 0, 'stop_cond': 1, 'hits_boundary': False}
+    if slack < 1e-25:                       # x = Y(-b) already on the boundary
+        info.update(stop_cond=2, hits_boundary=True)
+        if return_all:
+            trail.append(x)
+            info['allvecs'] = trail
+        return x, info
+    if tol is None:
+        tol = max(min(0.01 * np.sqrt(gg), 0.1 * gg), 1e-25)
+    cap = n - m
+    n_iter = cap if max_iter is None else min(max_iter, cap)
+    patience = cap if max_infeasible_iter is None else max_infeasible_iter
+    outside_for = 0
+    fallback = np.zeros_like(x)             # last point known to satisfy the bounds
+    for _ in range(max(n_iter, 0)):
+        if gg < tol:
+            info['stop_cond'] = 4
+            break
+        info['niter'] += 1
+        curv = Hp.dot(p)
+        if curv <= 0:                       # follow p to the boundary of the region
+            if np.isinf(trust_radius):
+                raise ValueError("Negative curvature not allowed for unrestrited problems.")
+            _, t_far, ok = box_sphere_intersections(x, p, lb, ub, trust_radius, entire_line=True)
+            if ok:
+                x = x + t_far * p
+            x = reinforce_box_boundaries(x, lb, ub)
+            info.update(stop_cond=3, hits_boundary=True)
+            break
+        alpha = gg / curv
+        x_new = x + alpha * p
+        if np.linalg.norm(x_new) >= trust_radius:      # leaves the ball: stop on it
+            _, frac, ok = box_sphere_intersections(x, alpha * p, lb, ub, trust_radius)
+            if ok:
+                x = x + frac * alpha * p
+            x = reinforce_box_boundaries(x, lb, ub)
+            info.update(stop_cond=2, hits_boundary=True)
+            break
+        outside_for = 0 if inside_box_boundaries(x_new, lb, ub) else outside_for + 1
+        if outside_for > 0:                 # remember where the segment leaves the box
+            _, frac, ok = box_sphere_intersections(x, alpha * p, lb, ub, trust_radius)
+            if ok:
+                fallback = reinforce_box_boundaries(x + frac * alpha * p, lb, ub)
+                outside_for = 0
+        if outside_for > patience:
+            break
+        if return_all:
+            trail.append(x_new)
+        g_new = Z.dot(r + alpha * Hp)
+        gg_new = np.linalg.norm(g_new) ** 2
+        p = -g_new + (gg_new / gg) * p
+        x, r = x_new, g_new                 # the projected residual is the one kept
+        gg = np.linalg.norm(g_new) ** 2
+        Hp = H.dot(p)
+    if not inside_box_boundaries(x, lb, ub):
+        x = fallback
+        info['hits_boundary'] = True
+    if return_all:
+        info['allvecs'] = trail
+    return x, info

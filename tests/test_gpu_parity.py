@@ -400,22 +400,43 @@ def test_results_do_not_alias_across_calls(dev):
     assert np.array_equal(x3, keep) and np.array_equal(x1, keep)
 
 
-def test_rank_deficient_jacobian_fails_loudly(dev):
-    """A with a repeated row: A A' is singular.  Z x only needs a consistent
-    system and still works; Y b with b outside the range of A has no solution
-    -- the reference's factorisation raises and falls back to a dense SVD
-    (projections.py:101-108), the device path raises InnerSolveError instead of
-    returning garbage."""
+def test_rank_deficient_jacobian_gives_the_pseudo_inverse(dev):
+    """A with a repeated row: A A' is singular.  The reference's factorisation
+    raises and it falls back to dense SVD maps, i.e. the pseudo-inverse
+    (projections.py:101-108, :236-287); the device path recovers the same maps
+    by CG on the squared operator: Z x is the projection onto null(A), Y b and
+    LS x the minimum-norm least-squares solutions."""
     rng = np.random.RandomState(0)
     A = sps.random(40, 200, density=0.05, random_state=rng, format='csr')
     A = sps.vstack([A, A[3]]).tocsr()                 # row 40 == row 3
+    Ad = A.toarray()
     Z, LS, Y = dev.projections(A)
     x = rng.standard_normal(200)
     z = Z.dot(x)
     assert np.linalg.norm(A.dot(z)) <= 1e-10 * np.linalg.norm(x)
+    assert_close(z, x - np.linalg.pinv(Ad).dot(Ad.dot(x)), 1e-8)
     b = rng.standard_normal(41)                       # b[40] != b[3]: inconsistent
-    with pytest.raises(dev.device.InnerSolveError):
-        Y.dot(b)
+    assert_close(Y.dot(b), np.linalg.pinv(Ad).dot(b), 1e-7)
+    assert_close(Ad.T.dot(LS.dot(x)), np.linalg.pinv(Ad).dot(Ad.dot(x)), 1e-7)
+
+
+def test_opaque_hessian_runs_the_host_loop(dev, kat):
+    """H given as a bare LinearOperator (reference _minimize_constrained.py:
+    404-406): the recurrence runs on the host around device projections and
+    gives the answers of the known-answer cases."""
+    from scipy.sparse.linalg import LinearOperator
+    for name in ("nocedal_16_2", "hits_boundary", "box_active_maxiter", "neg_curv"):
+        H, A, c, b, kw, exc = cases.PCG_CASES[name]
+        Hm = np.array(H, float)
+        Hop = LinearOperator(Hm.shape, matvec=lambda v, Hm=Hm: Hm.dot(v), dtype=np.float64)
+        Z, _, Y = dev.projections(sps.csc_matrix(np.array(A, float)))
+        kw = dict(kw)
+        kw.pop("return_all", None)
+        x, info = dev.qp.projected_cg(Hop, np.array(c, float), Z, Y, np.array(b, float), **kw)
+        ref = kat["pcg"][name]
+        assert (info["niter"], info["stop_cond"], info["hits_boundary"]) == \
+            (ref["niter"], ref["stop_cond"], ref["hits_boundary"])
+        assert_close(x, ref["x"], 1e-9)
 
 
 # ------------------------------------------------------------------ banded direct solve
