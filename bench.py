@@ -201,9 +201,40 @@ def end_to_end_solve(n, hot_path=None):
                                    method='equality_constrained_sqp', hot_path=hot_path)
     dt = time.perf_counter() - t0
     return {"n": n, "m": n // 2, "seconds": dt, "niter": int(res.niter),
-            "cg_niter": int(res.cg_niter), "status": int(res.status),
-            "optimality": float(res.optimality),
+            "cg_niter": int(res.cg_niter), "nfev": int(res.nfev), "status": int(res.status),
+            "optimality": float(res.optimality), "fun": float(res.fun),
             "constr_violation": float(res.constr_violation)}
+
+
+def reference_record(name):
+    """What the unmodified reference gave for a named end-to-end problem in the
+    build container (tests/golden/e2e_large.npz, made by make_golden_large.py)."""
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "e2e_large.npz"))
+        s = g[name + "/scalars"]
+        return {"niter": int(s[0]), "cg_niter": int(s[1]), "status": int(s[2]), "nfev": int(s[3]),
+                "optimality": float(s[4]), "constr_violation": float(s[5]), "fun": float(s[6]),
+                "seconds": float(s[8]),
+                "where": "unmodified reference, build container CPU (scipy SuperLU), golden record"}
+    except Exception as exc:
+        return {"unavailable": str(exc)}
+
+
+def named_solve(name):
+    """BASELINE configs 3 / 4 through the public API (tests/e2e_problems.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import e2e_problems
+    import ipsolver_b200 as ipb
+    api = dict(minimize_constrained=ipb.minimize_constrained,
+               LinearConstraint=ipb.LinearConstraint, BoxConstraint=ipb.BoxConstraint,
+               NonlinearConstraint=ipb.NonlinearConstraint)
+    t0 = time.perf_counter()
+    res = e2e_problems.LARGE_PROBLEMS[name](api)()
+    dt = time.perf_counter() - t0
+    return {"problem": name, "seconds": dt, "niter": int(res.niter), "cg_niter": int(res.cg_niter),
+            "nfev": int(res.nfev), "status": int(res.status), "optimality": float(res.optimality),
+            "fun": float(res.fun), "constr_violation": float(res.constr_violation),
+            "reference": reference_record(name)}
 
 
 def run_reference(args):
@@ -492,9 +523,18 @@ def run_b200(args):
     solve = None
     if args.solve_n > 0:
         solve = {"b200": end_to_end_solve(args.solve_n),
-                 "what": "minimize_constrained(method='equality_constrained_sqp') on the "
-                         "synthetic convex QP, outer loop on the host, every linear-algebra "
-                         "step on the device"}
+                 "what": "BASELINE config 2: minimize_constrained(method='equality_constrained_sqp') "
+                         "on the synthetic convex QP, outer loop on the host, every linear-algebra "
+                         "step on the device, vectors resident across the iteration"}
+        if args.solve_n == 1_000_000:
+            solve["reference"] = reference_record("eqp_window_1000000")
+        for key, name in (("config3_interior_point", args.solve_config3),
+                          ("config4_thomson", args.solve_config4)):
+            if name and name != "none":
+                try:
+                    solve[key] = named_solve(name)
+                except Exception as exc:          # never lose the headline over an extra
+                    solve[key] = {"problem": name, "error": repr(exc)}
         if not args.no_cpu and args.solve_cpu_n > 0:
             import oracle
             solve["cpu_oracle"] = end_to_end_solve(args.solve_cpu_n, oracle.host_hot_path())
@@ -710,6 +750,13 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--solve-n", type=int, default=1_000_000,
                     help="size of the end-to-end SQP solve (0: skip)")
+    ap.add_argument("--solve-config3", default="ipqp_window_100000",
+                    help="tr_interior_point run reported under end_to_end_solve (tests/"
+                         "e2e_problems.py LARGE_PROBLEMS; 'ipqp_window_1000000' = BASELINE config "
+                         "3 at full size, minutes; 'none' to skip)")
+    ap.add_argument("--solve-config4", default="thomson_500_equals",
+                    help="Thomson run reported under end_to_end_solve ('thomson_2000_equals' = "
+                         "BASELINE config 4 at full size, minutes; 'none' to skip)")
     ap.add_argument("--solve-cpu-n", type=int, default=100_000,
                     help="size of the same solve on the CPU oracle (0: skip)")
     args = ap.parse_args()
