@@ -520,21 +520,22 @@ def run_b200(args):
         ref_cfg = gpu_run_at(args.cpu_n, args)
 
     # ---- end-to-end solve (BASELINE config 2: n = 1e6 through the SQP outer loop)
-    solve = None
+    solve = {}
     if args.solve_n > 0:
-        solve = {"b200": end_to_end_solve(args.solve_n),
-                 "what": "BASELINE config 2: minimize_constrained(method='equality_constrained_sqp') "
+        solve["b200"] = end_to_end_solve(args.solve_n)
+        solve["what"] = ("BASELINE config 2: minimize_constrained(method='equality_constrained_sqp') "
                          "on the synthetic convex QP, outer loop on the host, every linear-algebra "
-                         "step on the device, vectors resident across the iteration"}
+                         "step on the device, vectors resident across the iteration")
         if args.solve_n == 1_000_000:
             solve["reference"] = reference_record("eqp_window_1000000")
-        for key, name in (("config3_interior_point", args.solve_config3),
-                          ("config4_thomson", args.solve_config4)):
-            if name and name != "none":
-                try:
-                    solve[key] = named_solve(name)
-                except Exception as exc:          # never lose the headline over an extra
-                    solve[key] = {"problem": name, "error": repr(exc)}
+    for key, name in (("config3_interior_point", args.solve_config3),
+                      ("config4_thomson", args.solve_config4)):
+        if name and name != "none":
+            try:
+                solve[key] = named_solve(name)
+            except Exception as exc:          # never lose the headline over an extra
+                solve[key] = {"problem": name, "error": repr(exc)}
+    if args.solve_n > 0:
         if not args.no_cpu and args.solve_cpu_n > 0:
             import oracle
             solve["cpu_oracle"] = end_to_end_solve(args.solve_cpu_n, oracle.host_hot_path())

@@ -658,6 +658,7 @@ __device__ __forceinline__ void block_rows(const Stage &st, const BlockDesc &d,
     const int *rp = st.rowptr - r0a;          // rp[r], r a global row index
     const double *xv = XS ? (st.xs - d.c0) : x;   // xv[c], c a global column index
     const bool dot_is_x = XS && (e.dotv == x);
+#pragma unroll 1
     for (int r = d.r0 + (int)threadIdx.x; r < d.r1; r += THREADS) {
         int q = rp[r];
         const int qe = rp[r + 1];
@@ -668,6 +669,10 @@ __device__ __forceinline__ void block_rows(const Stage &st, const BlockDesc &d,
         }
         if (!FAST && e.addv) avv = so ? so[r] : e.addv[r];
         double sum = 0.0;
+        // rows are short (1.4 - 5 entries): the compiler's default 16-fold unrolling of
+        // this loop costs a cascade of remainder branches per row (~160 warp
+        // instructions for a 1-entry row); keep it tight
+#pragma unroll 1
         for (; q + 1 < qe; q += 2) {
             const int c0 = sc[q], c1 = sc[q + 1];
             const double v0 = sv[q], v1 = sv[q + 1];

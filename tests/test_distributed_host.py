@@ -159,3 +159,38 @@ def test_generated_parts_equal_sliced_parts(n, size):
         assert np.array_equal(cl, c[n0:n1]) and np.array_equal(bl, b[m0:m1])
         fro2 += w["fro2_own"]
     assert np.sqrt(fro2) == pytest.approx(a["fro"], rel=1e-13)
+
+
+@pytest.mark.parametrize("size", [2, 3, 8])
+def test_band_window_of_a_rank_solves_like_the_global_factor(size):
+    """Banded direct solve on row-partitioned ranks (host model): every rank
+    factorises its own rows of M = A~ A~' plus a margin and sweeps with 48 halo
+    rows of its neighbours' right-hand side; the own rows of the result equal
+    the global solve to round-off, the m-space ghost zones are exactly the
+    contiguous halo rows and the window equals the slice of the global M."""
+    import scipy.sparse.linalg as spla
+    n = 6000
+    H, A, c, b = synthetic.make_qp(n, "window", 1e2, seed=0)
+    m = A.shape[0]
+    part = D.RowPartition(n, m, size)
+    d = 1.0 / np.sqrt(np.asarray(A.multiply(A).sum(axis=1)).ravel())
+    An = sps.csr_matrix(sps.diags(d) @ A)
+    M = sps.csr_matrix(An @ An.T)
+    rhs = np.random.RandomState(3).standard_normal(m)
+    v_ref = spla.spsolve(M.tocsc(), rhs)
+    for g in range(size):
+        parts = D.local_parts(part, g, H, A)
+        bd = parts["band"]
+        assert bd is not None
+        m0, m1 = part.own(g, 1)
+        e0, e1, gb, ga = D.band_window(part, g)
+        lo, hi = parts["ghosts"][1]
+        assert np.array_equal(lo, np.arange(m0 - gb, m0)) and np.array_equal(hi, np.arange(m1, m1 + ga))
+        assert bd["ext_off"] == m0 - e0
+        assert abs(bd["M_ext"] - M[e0:e1, e0:e1]).max() < 1e-15
+        # what the device does: exact solve on the window [own - halo, own + halo) with the
+        # right-hand side known there (zero beyond), keep the own rows
+        w0, w1 = m0 - gb, m1 + ga
+        v_loc = spla.spsolve(M[w0:w1, w0:w1].tocsc(), rhs[w0:w1])
+        err = np.linalg.norm(v_loc[m0 - w0:m1 - w0] - v_ref[m0:m1]) / np.linalg.norm(v_ref[m0:m1])
+        assert err < 1e-13
