@@ -44,13 +44,14 @@ UNIT = "it/s"
 
 
 def algorithmic_bytes(n, m, nnzH, nnzA, nnzM, niter, inner_iters, n_solves, n_refin, n_hp,
-                     n_sweeps=0, has_b=1):
+                     n_sweeps=0, has_b=1, fused_hp=0):
     """Compulsory HBM bytes of one launch of the solve kernel, for the
     algorithm AS RUN.  8-byte values, 4-byte indices,
     every matrix / vector counted once per logical read or write:
 
       B_spmv(rows, cols, nnz) = 12 nnz + 4 (rows+1) + 8 cols + 8 rows
-      outer iteration = B_H + 72 n  (+ its Z apply)
+      outer iteration = B_H + 72 n  (+ its Z apply); 64 n when p = -g + beta p is
+                formed inside H p (fused_hp: g read + p written; p read is B_H's x)
       Z apply = 2 B_A + B_At + 8 n  (A~ x, z = x - A~' v with the re-read of x,
                 the orthogonality product A z)  + its (A A')^-1 solve
       (A A')^-1 by the banded direct solve (n_sweeps > 0):
@@ -88,7 +89,8 @@ def algorithmic_bytes(n, m, nnzH, nnzA, nnzM, niter, inner_iters, n_solves, n_re
         solves = inner_iters * B_in
         refin = n_refin * z_products
         parts.update(B_in=B_in)
-    rest = n_z * z_products + n_y * (24 * m + B_At) + n_hp * B_H + niter * 72 * n
+    iter_vec = (64 if fused_hp else 72) * n
+    rest = n_z * z_products + n_y * (24 * m + B_At) + n_hp * B_H + niter * iter_vec
     total = solves + refin + rest
     survey = (n_solves + n_refin) * 35 * B_in_survey + (n_z + n_refin) * (z_products + 8 * n) \
         + n_hp * B_H + niter * 72 * n
@@ -305,6 +307,17 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def timeline_names(info):
+    """Phases between the grid barriers of one outer iteration (banded path)."""
+    if int(info.n_sweeps) <= 0:
+        return None
+    names = ["x+=alpha p; r+=alpha Hp", "rhs = A~ r", "banded sweep", "g = r - A~' v",
+             "A g (orthogonality)"]
+    if int(info.reserved) == 1:
+        return names + ["H p with p = -g + beta p formed on the fly"]
+    return names + ["p = -g + beta p", "H p"]
+
+
 def x_checksum(x):
     """Order-independent fingerprint of the solution, printed by every N so
     that the driver's own records show N-GPU = 1-GPU: ||x||_2, sum(x) and a
@@ -403,7 +416,7 @@ def run_b200(args):
     band = proj.band_info
     bytes_launch, bytes_survey, parts = algorithmic_bytes(
         n, m, H.nnz, A.nnz, nnzM, int(i0.niter), int(i0.inner_iters), int(i0.n_solves),
-        int(i0.n_refinements), int(i0.n_spmv_h), int(i0.n_sweeps))
+        int(i0.n_refinements), int(i0.n_spmv_h), int(i0.n_sweeps), fused_hp=int(i0.reserved))
     avg_ms = float(np.mean(kernel_ms))
     peak, peak_src = peaks()
     achieved = bytes_launch / (avg_ms * 1e-3) / 1e9
@@ -456,12 +469,11 @@ def run_b200(args):
         stamps = ctx.trace_read().astype(np.int64)
         ctx.trace(0)
         d_us = np.diff(stamps) / 1e3
-        per_it = 7 if int(i0.n_sweeps) > 0 else None
+        names = timeline_names(i0)
+        per_it = len(names) if names else None
         tl = {"barriers": int(len(stamps)), "sum_ms": float(d_us.sum() / 1e3)}
         if per_it and len(d_us) >= per_it * int(i0.niter):
             last = d_us[-per_it * int(i0.niter):].reshape(int(i0.niter), per_it)
-            names = ["x+=alpha p; r+=alpha Hp", "rhs = A~ r", "banded sweep", "g = r - A~' v",
-                     "A g (orthogonality)", "p = -g + beta p", "H p"]
             tl["per_iteration_us"] = {k: float(v) for k, v in zip(names, np.median(last, axis=0))}
         roofline["timeline"] = tl
     except Exception as exc:          # measurement aid only
@@ -659,7 +671,7 @@ def run_b200_dist(args):
     nnzM, nnzH, nnzA = (int(v) for v in nnz_loc.tolist())
     bytes_launch, bytes_survey, parts = algorithmic_bytes(
         n, m, nnzH, nnzA, nnzM, int(i0.niter), int(i0.inner_iters), int(i0.n_solves),
-        int(i0.n_refinements), int(i0.n_spmv_h), int(i0.n_sweeps))
+        int(i0.n_refinements), int(i0.n_spmv_h), int(i0.n_sweeps), fused_hp=int(i0.reserved))
     t = torch.tensor([float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     avg_ms = float(t.item())
@@ -676,10 +688,9 @@ def run_b200_dist(args):
         d_us = np.diff(stamps) / 1e3
         timeline = {"barriers": int(len(stamps)), "sum_ms": float(d_us.sum() / 1e3),
                     "kernel_ms": float(inf_t.kernel_ms)}
-        if int(i0.n_sweeps) > 0 and len(d_us) >= 7 * int(i0.niter):
-            last = d_us[-7 * int(i0.niter):].reshape(int(i0.niter), 7)
-            names = ["x+=alpha p; r+=alpha Hp", "rhs = A~ r", "banded sweep", "g = r - A~' v",
-                     "A g (orthogonality)", "p = -g + beta p", "H p"]
+        names = timeline_names(i0)
+        if names and len(d_us) >= len(names) * int(i0.niter):
+            last = d_us[-len(names) * int(i0.niter):].reshape(int(i0.niter), len(names))
             timeline["per_iteration_us"] = {k: float(v) for k, v in zip(names, np.median(last, axis=0))}
     except Exception as exc:
         timeline = {"error": str(exc)}

@@ -62,7 +62,7 @@ typedef struct {
     double  kernel_ms;        /* device time of the solve kernel (CUDA events)   */
     int64_t n_sweeps;         /* sweeps of the banded direct solve (0: CG only)  */
     int32_t n_fallbacks;      /* banded solves given up for the CG (0 normally)  */
-    int32_t reserved;
+    int32_t reserved;         /* 1: the update p = -g + beta p ran inside H p     */
 } ipb_pcg_info;
 
 /* Counters of one projector application (Z, LS or Y). */

@@ -30,6 +30,7 @@ struct ipb_csr {
     double *val = nullptr;
     int4 *desc = nullptr;
     int nblk = 0;
+    int xform_ok = 0;               // see CsrView::xform_ok (square matrices only)
     bool has_t = false;
     int *t_rowptr = nullptr, *t_col = nullptr, *perm = nullptr;
     double *t_val = nullptr;
@@ -217,6 +218,7 @@ static void vfree(ipb_ctx *ctx, double *p) {
 static CsrView csr_view(const ipb_csr *m, const double *val_override = nullptr) {
     CsrView v;
     v.rows = m->rows; v.cols = m->cols; v.nblk = m->nblk; v.desc = m->desc; v.space = m->space;
+    v.xform_ok = m->xform_ok;
     v.rowptr = m->rowptr; v.col = m->col;
     v.val = val_override ? val_override : m->val;
     return v;
@@ -225,6 +227,7 @@ static CsrView csr_view(const ipb_csr *m, const double *val_override = nullptr) 
 static CsrView csr_view_t(const ipb_csr *m, const double *val_override = nullptr) {
     CsrView v;
     v.rows = m->cols; v.cols = m->rows; v.nblk = m->t_nblk; v.desc = m->t_desc; v.space = 1 - m->space;
+    v.xform_ok = 0;
     v.rowptr = m->t_rowptr; v.col = m->t_col;
     v.val = val_override ? val_override : m->t_val;
     return v;
@@ -559,6 +562,17 @@ extern "C" int ipb_csr_create(ipb_ctx *ctx, int64_t rows, int64_t cols, int64_t 
     if (rows == 0) CU(ctx, cudaMemsetAsync(m->rowptr, 0, sizeof(int), ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if ((s = build_blocks(ctx, m->rowptr, m->col, m->rows, m->cols, &m->desc, &m->nblk)) != IPB_OK) return s;
+    if (rows == cols && m->nblk > 0) {
+        int *d_bad = nullptr, bad = 0;
+        if ((s = dalloc(ctx, &d_bad, 1)) != IPB_OK) return s;
+        CU(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+        k_block_xform_ok<<<cdiv(m->nblk, 256), 256, 0, ctx->stream>>>(m->nblk, m->desc, d_bad);
+        ctx->launches += 1;
+        CU(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_bad);
+        m->xform_ok = bad ? 0 : 1;
+    }
     if (with_transpose) {
         s = build_transpose(ctx, m);
         if (s != IPB_OK) return s;
@@ -1093,7 +1107,7 @@ static ProjView proj_view(const ipb_proj *p) {
     v.At = csr_view_t(p->A, p->nt_val);
     v.has_M = p->has_M ? 1 : 0;
     if (p->has_M) {
-        v.M.space = 1;
+        v.M.space = 1; v.M.xform_ok = 0;
         v.M.rows = v.m; v.M.cols = v.m; v.M.nblk = p->m_nblk; v.M.desc = p->m_desc;
         v.M.rowptr = p->m_rowptr; v.M.col = p->m_col; v.M.val = p->m_val;
     }
@@ -1257,7 +1271,8 @@ static int run_pcg(ipb_ctx *ctx, const ipb_hess *H, ipb_proj *P, const double *d
         info->n_solves = h->n_solves; info->n_refinements = h->n_refinements;
         info->n_spmv_h = h->n_spmv_h; info->max_orth = h->max_orth;
         info->tol_used = h->tol_used; info->kernel_ms = ms;
-        info->n_sweeps = h->n_sweeps; info->n_fallbacks = h->n_fallbacks; info->reserved = 0;
+        info->n_sweeps = h->n_sweeps; info->n_fallbacks = h->n_fallbacks;
+        info->reserved = h->fused_hp;          // 1: p = -g + beta p was formed inside H p
     }
     if (h->status == IPB_ERR_TR_INFEASIBLE)
         IPB_FAIL(ctx, IPB_ERR_TR_INFEASIBLE, "Trust region problem does not have a solution.");

@@ -66,6 +66,8 @@ struct CsrView {
     int rows, cols;
     int space;                // vector space of the columns (0: n, 1: m) -- selects the halo list
     int nblk;                 // row blocks (built at upload, <= CHUNK nnz each)
+    int xform_ok;             // square, every block stages its x slice, owns its rows' columns and has
+                              // room for a second slice: x may be formed on the fly (spmv xform)
     const int4 *desc;         // per block {r0, r1, p0, len}, {c0, xcnt, -, -}
     const int *rowptr;
     const int *col;
@@ -544,11 +546,18 @@ struct Epi {
     int want_sq;
     int accumulate;
     int want_psq;             // acc0 += (y_r * post[r])^2 (dotv unused then)
+    // x formed on the fly (EK_FAST, matrices with xform_ok): the product is taken
+    // with  x' = -xg + xbeta * x  and x' is written to xout for the rows of each
+    // block -- the update p = -g + beta p of projected CG fused into H p
+    const double *xg;
+    double xbeta;
+    double *xout;
 };
 
 __device__ __forceinline__ Epi epi_plain(double *y) {
     Epi e; e.y = y; e.addv = nullptr; e.sa = 1.0; e.sb = 0.0; e.dotv = nullptr;
-    e.wv = nullptr; e.post = nullptr; e.want_sq = 0; e.accumulate = 0; e.want_psq = 0; return e;
+    e.wv = nullptr; e.post = nullptr; e.want_sq = 0; e.accumulate = 0; e.want_psq = 0;
+    e.xg = nullptr; e.xbeta = 0.0; e.xout = nullptr; return e;
 }
 
 // addv[r] and dotv[r] are passed in (fetched together with the gathers, so
@@ -612,7 +621,8 @@ static_assert(((XMAX - OPND_MAX) * 8) % 16 == 0 && ((CHUNK + PAD - OPND_MAX) * 8
 // so that the parity of every slot keeps advancing once per use.
 __device__ __forceinline__ void stage_issue(const CsrView &M, const BlockDesc d,
                                             const double *x, bool xstage,
-                                            Smem &sm, int s, const double *opnd = nullptr) {
+                                            Smem &sm, int s, const double *opnd = nullptr,
+                                            const double *xg = nullptr) {
     if (d.len <= CHUNK) {
         const int p0a = d.p0 & ~3, r0a = d.r0 & ~3;
         const unsigned cnt = (unsigned)((d.p0 + d.len - p0a + 3) & ~3);
@@ -627,9 +637,11 @@ __device__ __forceinline__ void stage_issue(const CsrView &M, const BlockDesc d,
         const int oslot = opnd ? opnd_slot(d, xstage) : 0;
         const unsigned ocnt = oslot ? (unsigned)((d.r1 - r0a + 3) & ~3) : 0u;
         unsigned tx = cnt * 12u + rcnt * 4u + xcnt * 8u + ocnt * 8u;
+        if (xg) tx += xcnt * 8u;        // second slice (xform): same columns, in the xs-tail slot
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                      ::"r"(smem_addr(&sm.full[s])), "r"(tx) : "memory");
         if (ocnt) bulk_g2s(const_cast<double *>(opnd_ptr(st, oslot)), opnd + r0a, ocnt * 8u, &sm.full[s]);
+        if (xg && xcnt) bulk_g2s(const_cast<double *>(opnd_ptr(st, 1)), xg + d.c0, xcnt * 8u, &sm.full[s]);
         bulk_g2s(st.val, M.val + p0a, cnt * 8u, &sm.full[s]);
         bulk_g2s(st.col, M.col + p0a, cnt * 4u, &sm.full[s]);
         bulk_g2s(st.rowptr, M.rowptr + r0a, rcnt * 4u, &sm.full[s]);
@@ -645,11 +657,21 @@ __device__ __forceinline__ void stage_issue(const CsrView &M, const BlockDesc d,
 // two products inside the CG loops.  Entries are added in index order -- the
 // left-to-right order of scipy's csr_matvec, so with -fmad=false row sums are
 // bit-identical to it.
-template <bool XS, bool FAST>
+// Epilogue kinds the products of the solve loops use, compiled without the
+// generic epilogue's run-time branches:
+//   EK_FAST  y = s (+ acc0 += s * dotv)            H p, M r, A' r
+//   EK_AXPY  y = addv - s, acc1 += y^2             g = r - A~' v
+//   EK_POST  y = s * post, acc1 += s^2, acc0 += y^2   D^-1/2 (A z)
+//   EK_SQ    y = s, acc1 += s^2                    rhs = A~ x
+//   EK_ANY   everything else (row_out)
+enum { EK_FAST = 0, EK_AXPY = 1, EK_POST = 2, EK_SQ = 3, EK_ANY = 4 };
+
+template <bool XS, int KIND>
 __device__ __forceinline__ void block_rows(const Stage &st, const BlockDesc &d,
                                            const double *x, const Epi &e, const double *opnd,
                                            bool xstage, double &acc0, double &acc1) {
     const int p0a = d.p0 & ~3, r0a = d.r0 & ~3;
+    constexpr bool FAST = KIND == EK_FAST;
     // staged slice of the epilogue operand (addv, else post), indexed by global row
     const int oslot = (!FAST && opnd) ? opnd_slot(d, xstage) : 0;
     const double *so = oslot ? opnd_ptr(st, oslot) - r0a : nullptr;
@@ -667,7 +689,7 @@ __device__ __forceinline__ void block_rows(const Stage &st, const BlockDesc &d,
             const unsigned off = (unsigned)(r - d.c0);
             dvv = (dot_is_x && off < (unsigned)d.xcnt) ? st.xs[off] : e.dotv[r];
         }
-        if (!FAST && e.addv) avv = so ? so[r] : e.addv[r];
+        if ((KIND == EK_AXPY || KIND == EK_ANY) && e.addv) avv = so ? so[r] : e.addv[r];
         double sum = 0.0;
         // rows are short (1.4 - 5 entries): the compiler's default 16-fold unrolling of
         // this loop costs a cascade of remainder branches per row (~160 warp
@@ -684,6 +706,18 @@ __device__ __forceinline__ void block_rows(const Stage &st, const BlockDesc &d,
         if (FAST) {
             if (e.dotv) acc0 += sum * dvv;
             e.y[r] = sum;
+        } else if (KIND == EK_AXPY) {
+            const double y = -sum + avv;          // the generic path's (-1 * s) + 1 * addv, bit for bit
+            acc1 += y * y;
+            e.y[r] = y;
+        } else if (KIND == EK_POST) {
+            const double yp = sum * (so ? so[r] : e.post[r]);
+            acc1 += sum * sum;
+            acc0 += yp * yp;
+            e.y[r] = yp;
+        } else if (KIND == EK_SQ) {
+            acc1 += sum * sum;
+            e.y[r] = sum;
         } else {
             row_out(e, r, sum, avv, dvv, (so && !e.addv) ? so[r] : (e.post ? e.post[r] : 1.0),
                     acc0, acc1);
@@ -694,7 +728,7 @@ __device__ __forceinline__ void block_rows(const Stage &st, const BlockDesc &d,
 // y = M x over the row blocks of M; CTA b takes the contiguous block range
 // [b*per, (b+1)*per).  Thread 0 starts the first NSTAGE copies; after that a
 // stage is refilled by the last warp that finishes with it.
-template <bool FAST>
+template <int KIND>
 __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const Epi e,
                                        Smem &sm, const SyncView &S, double &acc0,
                                        double &acc1) {
@@ -716,18 +750,20 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
     const bool xstage = (reinterpret_cast<size_t>(x) & 15) == 0;
     // epilogue operand staged with the blocks (never aliases y: a block's slice is
     // read before its rows are written, by the copy this CTA waits for)
+    constexpr bool FAST = KIND == EK_FAST;
     const double *opnd = FAST ? nullptr : (e.addv ? e.addv : e.post);
     if (opnd && (reinterpret_cast<size_t>(opnd) & 15) != 0) opnd = nullptr;
+    const double *xg = (FAST && M.xform_ok && xstage) ? e.xg : nullptr;
     if (M.space == 2) {
         // measurement only: the row arithmetic without the copy pipeline -- the
         // CTA's first block is staged once and processed nmine times
         const BlockDesc d0 = load_desc(dp, 0);
         if (d0.len > CHUNK) return;
-        if (tid == 0) stage_issue(M, d0, x, xstage, sm, base % NSTAGE, opnd);
+        if (tid == 0) stage_issue(M, d0, x, xstage, sm, base % NSTAGE, opnd, nullptr);
         mbar_wait(&sm.full[base % NSTAGE], (base / NSTAGE) & 1u, S.abort_flag);
         for (int j = 0; j < nmine; ++j) {
-            if (xstage && d0.xcnt > 0) block_rows<true, FAST>(sm.st[base % NSTAGE], d0, x, e, opnd, xstage, acc0, acc1);
-            else block_rows<false, FAST>(sm.st[base % NSTAGE], d0, x, e, opnd, xstage, acc0, acc1);
+            if (xstage && d0.xcnt > 0) block_rows<true, KIND>(sm.st[base % NSTAGE], d0, x, e, opnd, xstage, acc0, acc1);
+            else block_rows<false, KIND>(sm.st[base % NSTAGE], d0, x, e, opnd, xstage, acc0, acc1);
         }
         __syncthreads();
         if (tid == 0) sm.seq = base + 1u;
@@ -737,7 +773,7 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
         for (int k = 0; k < NSTAGE && k < nmine; ++k) {
             const BlockDesc dk = load_desc(dp, IPB_BLK(k));
             if (dist && dk.ghost) ghost_wait(S, sm, M.space);
-            stage_issue(M, dk, x, xstage, sm, (base + k) % NSTAGE, opnd);
+            stage_issue(M, dk, x, xstage, sm, (base + k) % NSTAGE, opnd, xg);
         }
     BlockDesc d = load_desc(dp, IPB_BLK(0));
     for (int j = 0; j < nmine; ++j) {
@@ -747,9 +783,22 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
         const int s = u % NSTAGE;
         if (d.len <= CHUNK) {
             mbar_wait(&sm.full[s], (u / NSTAGE) & 1u, S.abort_flag);
+            if (FAST && xg) {
+                // form the block's x slice in place: x' = -g + beta x; the block's own
+                // rows of x' go to xout (blocks own the columns of their rows)
+                Stage &stw = sm.st[s];
+                const double *gs = opnd_ptr(stw, 1);
+                for (int i = tid; i < d.xcnt; i += THREADS) {
+                    const double v = -gs[i] + e.xbeta * stw.xs[i];
+                    stw.xs[i] = v;
+                    const int c = d.c0 + i;
+                    if (c >= d.r0 && c < d.r1) e.xout[c] = v;
+                }
+                __syncthreads();
+            }
             if (!e.y) { /* copy pipeline only (bench) */ }
-            else if (xstage && d.xcnt > 0) block_rows<true, FAST>(sm.st[s], d, x, e, opnd, xstage, acc0, acc1);
-            else block_rows<false, FAST>(sm.st[s], d, x, e, opnd, xstage, acc0, acc1);
+            else if (xstage && d.xcnt > 0) block_rows<true, KIND>(sm.st[s], d, x, e, opnd, xstage, acc0, acc1);
+            else block_rows<false, KIND>(sm.st[s], d, x, e, opnd, xstage, acc0, acc1);
         } else {
             // one long row: the whole CTA strides over it, fixed-order tree
             double part = 0.0;
@@ -777,7 +826,7 @@ __device__ __noinline__ void spmv_impl(const CsrView M, const double *x, const E
                 __threadfence_block();
                 if (j + NSTAGE < nmine) {
                     if (dist && dfar.ghost) ghost_wait(S, sm, M.space);
-                    stage_issue(M, dfar, x, xstage, sm, s, opnd);
+                    stage_issue(M, dfar, x, xstage, sm, s, opnd, xg);
                 }
             }
         }
@@ -792,10 +841,17 @@ __device__ __forceinline__ void spmv(const CsrView M, const double *x, const Epi
                                      Smem &sm, const SyncView &S, double &acc0,
                                      double &acc1) {
     if (S.C.size > 1) halo_sync(S, sm, x, M.space);
-    const bool fast = !e.addv && e.sa == 1.0 && !e.accumulate && !e.want_sq &&
-                      !e.post && !e.wv;
-    if (fast) spmv_impl<true>(M, x, e, sm, S, acc0, acc1);
-    else spmv_impl<false>(M, x, e, sm, S, acc0, acc1);
+    const bool base = !e.accumulate && !e.wv && !e.dotv;
+    if (!e.addv && e.sa == 1.0 && !e.accumulate && !e.want_sq && !e.post && !e.wv)
+        spmv_impl<EK_FAST>(M, x, e, sm, S, acc0, acc1);
+    else if (base && e.addv && e.sa == -1.0 && e.sb == 1.0 && e.want_sq && !e.post)
+        spmv_impl<EK_AXPY>(M, x, e, sm, S, acc0, acc1);
+    else if (base && !e.addv && e.sa == 1.0 && e.want_sq && e.post && e.want_psq)
+        spmv_impl<EK_POST>(M, x, e, sm, S, acc0, acc1);
+    else if (base && !e.addv && e.sa == 1.0 && e.want_sq && !e.post)
+        spmv_impl<EK_SQ>(M, x, e, sm, S, acc0, acc1);
+    else
+        spmv_impl<EK_ANY>(M, x, e, sm, S, acc0, acc1);
 }
 
 // Dense row-major GEMV, one warp per row, same epilogue.
@@ -824,6 +880,33 @@ __device__ __noinline__ void gemv_dense(const double *D, int nx, const double *x
 
 // y = H x  with optional  acc0 += y.dotv.  Phases that accumulate into y are
 // separated by a grid barrier because row->CTA maps differ between terms.
+// H can form its argument on the fly (see Epi::xg): CSR term only (+ diagonal
+// tail), single GPU.
+__device__ __forceinline__ bool hess_can_xform(const HessView &H, const SyncView &S) {
+    return H.has_csr && !H.has_dense && H.S.xform_ok && S.C.size == 1 && H.nx > 0;
+}
+
+// y = H p' with p' = -g + beta p formed on the fly and written to pout (the
+// update of projected CG, qp_subproblem.py:628, fused into the product of
+// :634);  acc0 += p'.y.  Requires hess_can_xform.
+__device__ __noinline__ void hess_apply_xform(const HessView &H, const SyncView &S,
+                                              const double *g, const double *p, double beta,
+                                              double *pout, double *y, Smem &sm, double &acc0) {
+    double dummy = 0.0;
+    Epi e = epi_plain(y);
+    e.dotv = p;                  // = the staged x: the dot is taken with the transformed slice
+    e.xg = g; e.xbeta = beta; e.xout = pout;
+    spmv(H.S, p, e, sm, S, acc0, dummy);
+    const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
+    for (int i = H.nx + gt; i < H.n; i += nt) {
+        const double pn = -g[i] + beta * p[i];
+        pout[i] = pn;
+        const double v = H.has_tail ? H.tail[i - H.nx] * pn : 0.0;
+        y[i] = v;
+        if (H.has_tail) acc0 += v * pn;
+    }
+}
+
 __device__ __noinline__ void hess_apply(const HessView &H, const SyncView &S,
                                         const double *x, double *y,
                                         const double *dotv, Smem &sm,
@@ -1708,6 +1791,7 @@ struct PcgArgs {
         int x_slot;                    // 0: result in x, 1: xn, 2: xfeas
         int n_fallbacks;               // banded direct solves given up for CG
         long long n_sweeps;            // banded sweeps (direct solves incl. refinement)
+        int fused_hp;                  // p = -g + beta p was formed inside H p
     } *result;
 };
 
@@ -1732,6 +1816,8 @@ k_projected_cg(const PcgArgs a) {
     const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
     ProjStats st = proj_stats_init(a.P);
     double *x = a.x, *xn = a.xn, *r = a.r, *p = a.p, *Hp = a.Hp;
+    double *tmpv = a.tmp;              // r_next; changes places with p when H p forms p on the fly
+    int fused_hp = 0;
     long long n_spmv_h = 0;
     int nvec = 0;
     int status = 0, stop_cond = 1, hits = 0;
@@ -1830,7 +1916,7 @@ k_projected_cg(const PcgArgs a) {
             double sq = 0.0, out = 0.0;
             if (!a.has_box) {
                 constexpr int TS = (int)((sizeof(Stage) / (4 * sizeof(double))) & ~(size_t)31);
-                TileIO<4> io = {{x, p, r, Hp}, {xn, nullptr, a.tmp, nullptr}};
+                TileIO<4> io = {{x, p, r, Hp}, {xn, nullptr, tmpv, nullptr}};
                 tile_pass<4>(sm, S, n, io, [&](double *t, int e) {
                     const double v = t[e] + alpha * t[TS + e];
                     t[e] = v;
@@ -1840,7 +1926,7 @@ k_projected_cg(const PcgArgs a) {
             } else {
                 constexpr int TS = (int)((sizeof(Stage) / (6 * sizeof(double))) & ~(size_t)31);
                 TileIO<6> io = {{x, p, r, Hp, a.lb, a.ub},
-                                {xn, nullptr, a.tmp, nullptr, nullptr, nullptr}};
+                                {xn, nullptr, tmpv, nullptr, nullptr, nullptr}};
                 tile_pass<6>(sm, S, n, io, [&](double *t, int e) {
                     const double v = t[e] + alpha * t[TS + e];
                     t[e] = v;
@@ -1888,22 +1974,30 @@ k_projected_cg(const PcgArgs a) {
             if (counter > max_inf) break;                            // :615-616
             store_allvec(a, nvec, xn);
             // g_next = Z r_next (:624);  r <- g_next (:632)
-            double gg2 = null_space(a.P, S, sm, st, a.tmp, r);
+            double gg2 = null_space(a.P, S, sm, st, tmpv, r);
             double ng2 = sqrt(gg2);
             double rt_g_next = ng2 * ng2;                            // :626
             double beta = rt_g_next / rt_g;                          // :627
-            {                                                        // p = -g_next + beta p  (:628)
-                constexpr int TS = (int)((sizeof(Stage) / (2 * sizeof(double))) & ~(size_t)31);
-                TileIO<2> io = {{r, p}, {nullptr, p}};
-                tile_pass<2>(sm, S, n, io, [&](double *t, int e) {
-                    t[TS + e] = -t[e] + beta * t[TS + e];
-                });
-            }
             { double *t = x; x = xn; xn = t; x_slot ^= 1; }          // :630
             rt_g = rt_g_next;                                        // :633
-            grid_sync(S, sm);
-            acc0 = 0.0;                                              // :634
-            hess_apply(a.H, S, p, Hp, p, sm, acc0);
+            acc0 = 0.0;
+            if (hess_can_xform(a.H, S)) {
+                // p = -g_next + beta p (:628) formed inside H p (:634): the new p goes to
+                // the (now dead) r_next buffer, which then changes places with p
+                hess_apply_xform(a.H, S, r, p, beta, tmpv, Hp, sm, acc0);
+                { double *t = p; p = tmpv; tmpv = t; }
+                fused_hp = 1;
+            } else {
+                {                                                    // p = -g_next + beta p  (:628)
+                    constexpr int TS = (int)((sizeof(Stage) / (2 * sizeof(double))) & ~(size_t)31);
+                    TileIO<2> io = {{r, p}, {nullptr, p}};
+                    tile_pass<2>(sm, S, n, io, [&](double *t, int e) {
+                        t[TS + e] = -t[e] + beta * t[TS + e];
+                    });
+                }
+                grid_sync(S, sm);
+                hess_apply(a.H, S, p, Hp, p, sm, acc0);              // :634
+            }
             ++n_spmv_h;
             publish(S, sm, 0, acc0, OP_SUM);
             set_ops(sm, OP_SUM);
@@ -1937,6 +2031,7 @@ k_projected_cg(const PcgArgs a) {
         R.max_orth = st.max_orth; R.tol_used = tol;
         R.x_slot = final_slot;
         R.n_fallbacks = (int)st.n_fallbacks; R.n_sweeps = st.n_sweeps;
+        R.fused_hp = fused_hp;
     }
 }
 
@@ -2468,6 +2563,17 @@ __global__ void k_band_interleave(int m, int B, int ov, int steps, long long tot
     // rank factors its own rows plus a margin of its neighbours')
     const long long i = (g * 32 + lane) * B - ov + j + row_off;
     Lint[idx] = (i >= 0 && i < m) ? Lrow[i * HB + k] : (k == 0 ? 1.0 : 0.0);
+}
+
+// xform_ok of a square matrix: every block stages its x slice, the slice covers
+// the block's own rows and leaves room for a second slice of the same length
+__global__ void k_block_xform_ok(int nblk, const int4 *desc, int *bad) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const int4 a = desc[2 * (size_t)b], c = desc[2 * (size_t)b + 1];
+    const bool ok = a.w <= CHUNK && c.y > 0 && c.y <= OPND_MAX && c.y <= XMAX - OPND_MAX &&
+                    a.x >= c.x && a.y <= c.x + c.y;
+    if (!ok) atomicExch(bad, 1);
 }
 
 // column range of every row block -> {c0, xcnt} (second int4 of its descriptor)

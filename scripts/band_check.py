@@ -74,4 +74,4 @@ t = ctx.trace_read().astype(np.int64)
 ctx.trace(0)
 d = np.diff(t) / 1e3
 print("timeline: %d barriers, kernel %.3f ms, sum of phases %.3f ms" % (len(t), info.kernel_ms, d.sum() / 1e3))
-print("phases (us):", " ".join("%.0f" % v for v in d))
+print("phases (us):", " ".join("%.0f" % v for v in d), "| fused H p:", int(info.reserved))
