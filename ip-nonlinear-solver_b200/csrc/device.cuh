@@ -880,10 +880,9 @@ __device__ __noinline__ void gemv_dense(const double *D, int nx, const double *x
 
 // y = H x  with optional  acc0 += y.dotv.  Phases that accumulate into y are
 // separated by a grid barrier because row->CTA maps differ between terms.
-// H can form its argument on the fly (see Epi::xg): CSR term only (+ diagonal
-// tail), single GPU.
+// H can form its argument on the fly (see Epi::xg): CSR term only (+ diagonal tail).
 __device__ __forceinline__ bool hess_can_xform(const HessView &H, const SyncView &S) {
-    return H.has_csr && !H.has_dense && H.S.xform_ok && S.C.size == 1 && H.nx > 0;
+    return H.has_csr && !H.has_dense && H.S.xform_ok && H.nx > 0;
 }
 
 // y = H p' with p' = -g + beta p formed on the fly and written to pout (the
@@ -896,6 +895,10 @@ __device__ __noinline__ void hess_apply_xform(const HessView &H, const SyncView 
     Epi e = epi_plain(y);
     e.dotv = p;                  // = the staged x: the dot is taken with the transformed slice
     e.xg = g; e.xbeta = beta; e.xout = pout;
+    // row-partitioned: the slices reach into the neighbours' rows of BOTH vectors
+    // (spmv exchanges the ghosts of p; the ghost entries of p' are formed from
+    // them locally, bit-identical to the owner's)
+    if (S.C.size > 1) halo_sync(S, sm, g, H.S.space);
     spmv(H.S, p, e, sm, S, acc0, dummy);
     const int gt = blockIdx.x * THREADS + threadIdx.x, nt = gridDim.x * THREADS;
     for (int i = H.nx + gt; i < H.n; i += nt) {
