@@ -468,6 +468,29 @@ def test_band_solver_is_used_and_exact(dev):
     assert proj.band_info["trusted"]
 
 
+@pytest.mark.parametrize("chunk_rows, overlap", [(8, 0), (32, 64), (512, 0), (2048, 48)])
+def test_band_sweep_shapes(dev, chunk_rows, overlap):
+    """Chunk shapes away from the defaults: tiny chunks (more groups of chunks
+    than consumer warps on the machine: several rounds per warp), a wider
+    overlap, chunks longer than the default, one chunk longer than the matrix."""
+    n = 1_200_000 if chunk_rows == 8 else 60_000
+    H, A, c, b = synthetic.make_qp(n, "window", 1e2, seed=0)
+    dA = dev.device.DeviceCSR(dev.ctx, A, True)
+    proj = dev.device.DeviceProjector(dev.ctx, dA, aat_mode=2)
+    if not proj.band_info["in_use"]:
+        pytest.skip("no banded factor in this configuration")
+    y_ref = proj.row_space(b)
+    proj.set_band(0, chunk_rows, overlap)
+    info = proj.band_info
+    assert info["chunk_rows"] == chunk_rows and info["trusted"]
+    y = proj.row_space(b)
+    assert proj.last_info.n_fallbacks == 0 and proj.last_info.inner_iters == 1
+    assert_close(y, y_ref, 1e-12)
+    assert np.linalg.norm(A.dot(y) - b) <= 1e-12 * np.linalg.norm(b)
+    z = proj.null_space(c)
+    assert np.linalg.norm(A.dot(z)) <= 1e-13 * np.linalg.norm(c)
+
+
 def test_band_solver_falls_back_to_cg(dev):
     """A A' banded but with a non-decaying inverse: the chunked sweeps are not
     accurate, the residual check notices, the solve is redone by CG and the
