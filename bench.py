@@ -257,7 +257,9 @@ def run_reference(args):
                                           args.pattern, args.kappa)
     sample = ("oracle port of the reference path (scipy SuperLU AugmentedSystem + numpy), "
               "n=%d m=%d window A, %d steps x %d forced iterations in %.1f s; factorisation "
-              "%.1f s outside the timed region; 1 thread for factor/solve/SpMV"
+              "%.1f s outside the timed region; SuperLU factor / solve, csr_matvec and the "
+              "numpy loops are single-threaded (cores = 1), only BLAS dot / norm may use "
+              "blas_threads"
               % (n_s, n_s // 2, args.steps, args.iters, dt, t_factor))
     ran = argparse.Namespace(**vars(args))
     ran.n = n_s
@@ -273,7 +275,8 @@ def run_reference(args):
         "extrapolated": {"n": args.n, "value": its * n_s / args.n, "unit": UNIT,
                          "how": "per-iteration cost of the CPU path is linear in n for the "
                                 "windowed pattern; NOT a measurement"},
-        "cpu_baseline": {"value": its, "unit": UNIT, "cores": host_threads(),
+        "cpu_baseline": {"value": its, "unit": UNIT, "cores": 1,
+                         "blas_threads": host_threads(),
                          "kind": "port", "sample": sample, "host_cpus": os.cpu_count()},
         "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -531,7 +534,7 @@ def run_b200(args):
     if not args.no_cpu:
         its, dt, t_factor = cpu_reference_run(args.cpu_n, args.iters, args.cpu_steps, 0,
                                               args.pattern, args.kappa)
-        cpu = {"value": its, "unit": UNIT, "cores": host_threads(),
+        cpu = {"value": its, "unit": UNIT, "cores": 1, "blas_threads": host_threads(),
                "kind": "port",
                "sample": "oracle (scipy SuperLU AugmentedSystem + numpy) on the same workload "
                          "at n=%d (the reference cannot factorise n=%d: SuperLU fails, "

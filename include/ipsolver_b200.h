@@ -38,7 +38,7 @@ typedef enum {
     IPB_ERR_CUDA = 2,             /* CUDA runtime failure                          */
     IPB_ERR_TR_INFEASIBLE = 3,    /* qp_subproblem.py:516-517 (ValueError)         */
     IPB_ERR_NEG_CURVATURE = 4,    /* qp_subproblem.py:559-562 (ValueError)         */
-    IPB_ERR_INNER_SOLVE = 5,      /* inner CG on A A' broke down / did not converge */
+    IPB_ERR_INNER_SOLVE = 5,      /* no solver for (A A') v = rhs converged         */
     IPB_ERR_NOMEM = 6,
     IPB_ERR_COMM = 7              /* multi-GPU exchange failure / timeout          */
 } ipb_status;

@@ -1141,7 +1141,7 @@ static int run_proj(ipb_ctx *ctx, ipb_proj *p, int op, const double *din, double
         info->n_fallbacks = h->n_fallbacks; info->orth = h->orth; info->kernel_ms = ms;
     }
     if (h->status != 0)
-        IPB_FAIL(ctx, h->status, "inner CG on A A' broke down (status %d)", h->status);
+        IPB_FAIL(ctx, h->status, "no solver for (A A') v = rhs converged (status %d)", h->status);
     return IPB_OK;
 }
 

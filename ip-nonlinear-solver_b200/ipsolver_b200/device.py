@@ -15,7 +15,8 @@ from ._cabi import (DeviceLibraryError, PcgInfo, ProjInfo, dptr, f64,
 
 
 class InnerSolveError(RuntimeError):
-    """The inner CG on A A' broke down (singular / rank-deficient Jacobian)."""
+    """No solver for ``(A A') v = rhs`` converged: the banded direct solve, the CG
+    and the least-squares CG for singular ``A A'`` all failed."""
 
 
 class Context:
@@ -251,8 +252,8 @@ class DeviceHessian:
 
 
 class DeviceProjector:
-    """Z, LS, Y of ``projections.py:290`` with (A A')^-1 applied by CG on the
-    device.  Holds the device copy of A (and A')."""
+    """Z, LS, Y of ``projections.py:290`` with (A A')^-1 applied on the device
+    (banded direct solve or CG).  Holds the device copy of A (and A')."""
 
     def __init__(self, ctx, A, orth_tol=1e-12, max_refin=3, inner_rtol=1e-13,
                  inner_maxit=1000, aat_mode=0, band=(0, 0, 0)):

@@ -1,7 +1,9 @@
 """Device-backed ``projections()`` -- same signature, names and error
 behaviour as the reference (``ipsolver/_large_scale_constrained/
-projections.py:290-406``); ``(A A')^-1`` is an inner CG on the GPU instead of
-CHOLMOD / SuperLU / LAPACK.
+projections.py:290-406``); ``(A A')^-1`` is applied on the GPU -- by a banded
+Cholesky factor in overlapping chunks when ``A A'`` is banded, by an inner CG
+otherwise (or when a sweep's residual check fails) -- instead of CHOLMOD /
+SuperLU / LAPACK.
 
 Returned ``Z``, ``LS``, ``Y`` are ``scipy.sparse.linalg.LinearOperator``
 subclasses that carry the device projector (``.projector``), so
@@ -156,8 +158,9 @@ def projections(A, method=None, orth_tol=1e-12, max_refin=3, tol=1e-15):
     ``NormalEquation`` / ``AugmentedSystem``; dense A: ``QRFactorization`` /
     ``SVDFactorization``; the wrong family raises ``ValueError``), but every
     choice runs the same device algorithm: the normal-equation maps
-    ``Z = I - A'(AA')^-1 A``, ``LS = (AA')^-1 A``, ``Y = A'(AA')^-1`` with a
-    Jacobi-preconditioned CG on ``A A'`` and the reference's refinement loop
+    ``Z = I - A'(AA')^-1 A``, ``LS = (AA')^-1 A``, ``Y = A'(AA')^-1`` with the
+    banded direct solve / Jacobi-preconditioned CG on ``A A'`` (every solve
+    checked by its residual) and the reference's refinement loop
     (``orthogonality > orth_tol`` and at most ``max_refin`` rounds).  ``tol``
     (singular-value cut of the dense variants) has no device counterpart.
     """

@@ -3,7 +3,7 @@
 argument meaning and error behaviour), each call one persistent CUDA kernel.
 
 ``projected_cg`` runs the whole CG-Steihaug loop (H products, null-space
-projections with their inner CG on ``A A'``, reductions, sphere/box
+projections with their ``(A A')^-1`` solves, reductions, sphere/box
 intersections, termination logic) on the device; only ``x`` and the ``info``
 scalars return.
 """

@@ -5,10 +5,14 @@ golden results produced by the unmodified reference
 
 Tolerances (north_star): iteration counts +-1 and x, multipliers, optimality
 to 1e-8 relative where the run ends on a well-conditioned criterion (the
-``gtol=1e-6`` problems).  Runs that end by ``xtol`` stop when the trust region
-collapses in round-off and the barrier / Thomson runs
-take > 100 chaotic outer iterations, so for those the solution is compared
-(objective, feasibility, x where the minimiser is unique), not the counts."""
+``gtol=1e-6`` problems and the small classics: all reproduced count for count,
+x to 1e-15).  Runs that end by ``xtol`` stop when the trust region collapses
+in round-off and the barrier / Thomson runs take > 100
+outer iterations whose accept / reject decisions hang on the last bits of the
+merit function, so for those the solution is compared (objective,
+feasibility, optimality, x where the minimiser is unique) and the counts to
+the stated percentages.  BASELINE config 2 at n = 1e6 -- count for count --
+is in test_gpu_large.py."""
 import os
 
 import numpy as np
@@ -51,22 +55,36 @@ def test_sqp_counts_and_solution(api, gold, name):
 
 @pytest.mark.parametrize("name", ["eqp_window_2000", "eqp_rand_2000", "eqp_window_20000"])
 def test_sqp_xtol_runs_reach_the_same_point(api, gold, name):
-    fval = gold[name + "/scalars"][6]
+    """These runs do not meet gtol = 1e-8 cleanly: the reference wanders for 10-15
+    more iterations at optimality 2e-8 ... 2e-7 until the trust region has
+    collapsed (status 2), every accept / reject decided by round-off in the
+    merit function.  Two accurate solvers do not share that tail -- the device
+    run may even reach gtol (status 1) where the reference did not -- so the
+    POINT is compared: optimality at least as good as the reference's (golden),
+    x / multipliers / objective equal.  The n = 1e6 run of this family, whose
+    tail is reproduced count for count, is pinned in test_gpu_large.py."""
+    niter, cg, status, nfev, opt, viol, fval, radius = gold[name + "/scalars"]
     res = e2e_problems.PROBLEMS[name](api)()
     assert res.status in (1, 2)
-    assert res.optimality < 1e-6 and res.constr_violation < 1e-12
-    assert rel(res.x, gold[name + "/x"]) < 1e-7
-    assert rel(res.v, gold[name + "/v"]) < 1e-7
+    assert res.optimality <= max(1.5 * opt, 5e-8) and res.constr_violation < 1e-12
+    assert abs(res.niter - niter) <= 0.5 * niter and abs(res.cg_niter - cg) <= 0.5 * cg
+    assert rel(res.x, gold[name + "/x"]) < 5e-8
+    assert rel(res.v, gold[name + "/v"]) < 5e-8
     assert res.fun == pytest.approx(fval, rel=1e-12)
 
 
 @pytest.mark.parametrize("name", ["ipqp_window_1000", "ipqp_window_4000"])
 def test_interior_point_reaches_the_same_point(api, gold, name):
+    """~140 outer iterations over 10 barrier subproblems, most tangential steps
+    ending on the trust-region or slack boundary: counts agree to a few per
+    cent (outer) / tens of per cent (CG), the solution to 1e-6."""
     niter, cg, status, nfev, opt, viol, fval, radius = gold[name + "/scalars"]
     res = e2e_problems.PROBLEMS[name](api)()
     assert res.status == status == 1
     assert res.optimality < 1e-8 and res.constr_violation < 1e-8
     assert abs(res.niter - niter) <= 0.1 * niter
+    assert abs(res.cg_niter - cg) <= 0.4 * cg
+    assert abs(res.nfev - nfev) <= 0.1 * nfev
     assert rel(res.x, gold[name + "/x"]) < 1e-6
     assert res.fun == pytest.approx(fval, rel=1e-8)
 
