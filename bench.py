@@ -6,23 +6,29 @@ windowed 3-nnz/row A), one B200 (or N ranks under torchrun).
 A *step* is one ``projected_cg`` solve with exactly ``--iters`` CG iterations
 forced (``tol=1e-30, trust_radius=inf``) on a matrix
 already resident in HBM -- i.e. one pass of the hot path: 2 + iters
-null-space projections (each an inner CG on A A'), 1 row-space solve,
-1 + iters (+1) Hessian products and the fused vector updates, in ONE
-persistent kernel launch.
+null-space projections and 1 row-space solve (each one (A A')^-1 solve: a
+sweep of the banded direct solve, or an inner CG), 2 + iters Hessian products
+and the fused vector updates, in ONE persistent kernel launch.
 
   value  iterations/s with c, b, x resident in HBM (CUDA events on the
          library's stream, around the K steps)
   e2e    the same through the reference-facing Python API ``projected_cg(H, c,
          Z, Y, b, ...)`` with pinned HOST vectors: H2D of c and b, D2H of x and
-         the info struct inside the timed region (wall clock, synchronous API)
-  roofline   algorithmic bytes of the launch (formulas of
-         SURVEY.md section 8d applied to the launch's own counters) / the
-         launch's device time, against the measured HBM copy bandwidth
+         the info struct inside the timed region (wall clock, synchronous API);
+         ``e2e.pageable_inputs``: the same with ordinary numpy arrays
+  roofline   algorithmic bytes of the launch (applied to the
+         launch's own counters) / the launch's device time, against the measured
+         HBM copy bandwidth; ``roofline.timeline``: phase durations inside the
+         kernel (%globaltimer at every grid barrier)
   cpu_baseline   the oracle (scipy SuperLU + numpy restatement of the
-         reference path) on a bounded sample, host cores
+         reference path) on a bounded sample, host cores; ``reference_config_run``
+         is this arm on that same sample config
+  end_to_end_solve   BASELINE configs 2-4 through ``minimize_constrained`` next
+         to the reference's own records of the same problems
 
 ``--impl reference`` times only the CPU path (oracle port; the reference is
-pure Python and cannot travel to the GPU box).
+pure Python and cannot travel to the GPU box) on the largest size it can
+factorise, and says so (``same_config: false``).
 """
 import argparse
 import json
