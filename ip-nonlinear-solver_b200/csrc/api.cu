@@ -849,6 +849,19 @@ static void free_band(ipb_proj *p) {
     p->band = false; p->band_bw = -1; p->band_ngroup = 0;
 }
 
+// Owned rows per chunk.  A sweep costs max(bytes moved / HBM bandwidth, steps x
+// ~150 ns): 176 rows is the measured optimum when the bandwidth binds (m = 5e6:
+// 128 -> 186 us, 176 -> 171, 256 -> 177: longer chunks leave too few warps to
+// cover the per-step latency), and below ~3 groups of 32 chunks per SM the
+// chain length (2 B + 3 overlap steps) binds, so small problems (or the ranks
+// of a row-partitioned one) get shorter chunks, down to 64 rows.
+static int band_chunk_rows(const ipb_ctx *ctx, int64_t m) {
+    const int64_t groups = 3 * (int64_t)ctx->sms;
+    int B = (int)((m + 32 * groups - 1) / (32 * groups));
+    B = std::max(64, std::min(176, B));
+    return (B + 7) & ~7;
+}
+
 // Decide whether M is banded (half-bandwidth < HB) and size the chunked
 // factor: B owned rows per chunk such that the machine gets ~8 groups of 32
 // chunks per SM (enough bulk copies in flight to saturate HBM) without the
@@ -872,9 +885,7 @@ static int build_band(ipb_ctx *ctx, ipb_proj *p) {
     ov = (ov + 3) & ~3;
     int B = p->band_B_req;
     if (B <= 0) {
-        const int64_t groups = 6 * (int64_t)ctx->sms;
-        B = (int)((m + 32 * groups - 1) / (32 * groups));
-        B = std::max(64, std::min(512, B));
+        B = band_chunk_rows(ctx, m);
     }
     B = (B + 3) & ~3;
     const int64_t nchunk = (m + (int64_t)B - 1) / B;
@@ -948,9 +959,7 @@ extern "C" int ipb_proj_set_band_parts(ipb_ctx *ctx, ipb_proj *p, const ipb_csr 
     if (bw < 1 || bw >= HB) return IPB_OK;
     int B = chunk_rows;
     if (B <= 0) {
-        const int64_t groups = 6 * (int64_t)ctx->sms;
-        B = (int)((m + 32 * groups - 1) / (32 * groups));
-        B = std::max(64, std::min(512, B));
+        B = band_chunk_rows(ctx, m);
     }
     B = (B + 3) & ~3;
     const int64_t nchunk = (m + (int64_t)B - 1) / B;
