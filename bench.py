@@ -125,8 +125,29 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def count(self):
+        """Samples written so far (nvidia-smi needs ~0.1-0.3 s to start)."""
+        try:
+            with open(self.path) as fh:
+                return sum(1 for _ in fh)
+        except Exception:
+            return 0
+
+    def keep_loaded_until_sampling(self, step, min_samples=2, max_steps=400):
+        """Extra untimed warm-up steps until the sampler delivers: the timed
+        region of a fast step can be shorter than nvidia-smi's start-up, and a
+        line without clocks would be unusable.  Returns the steps spent."""
+        spent = 0
+        if self.proc is None:
+            return spent
+        while self.count() < min_samples and spent < max_steps:
+            step()
+            spent += 1
+        return spent
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
+               "window": "last warm-up steps + timed region (GPU under the same load throughout)"}
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -401,10 +422,12 @@ def run_b200(args):
     # ---- value: inputs resident in HBM
     dc, db = device.DeviceVector(ctx, c), device.DeviceVector(ctx, b)
     dx = device.DeviceVector(ctx, length=n)
-    for _ in range(args.warmup):
-        device.projected_cg_dev(proj, Hd, dc, db, dx, tol=1e-30, max_iter=args.iters)
     sampler = ClockSampler(ctx.device)
     sampler.start()
+    for _ in range(args.warmup):
+        device.projected_cg_dev(proj, Hd, dc, db, dx, tol=1e-30, max_iter=args.iters)
+    sampler.keep_loaded_until_sampling(
+        lambda: device.projected_cg_dev(proj, Hd, dc, db, dx, tol=1e-30, max_iter=args.iters))
     launches0 = ctx.launches
     kernel_ms, infos = [], []
     ctx.timer_start()
@@ -643,11 +666,20 @@ def run_b200_dist(args):
         ctx.sync()
         dist.barrier()
 
-    for _ in range(args.warmup):
-        S.projected_cg(dc, db, dx, tol=1e-30, max_iter=args.iters)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        S.projected_cg(dc, db, dx, tol=1e-30, max_iter=args.iters)
+    # every rank must run the same number of extra warm-up steps (the solves are
+    # collective): rank 0 decides, the others follow
+    more = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for _ in range(400):
+        more.fill_(1 if (rank == 0 and sampler.proc is not None and sampler.count() < 2) else 0)
+        dist.broadcast(more, src=0)
+        if int(more.item()) == 0:
+            break
+        S.projected_cg(dc, db, dx, tol=1e-30, max_iter=args.iters)
     launches0 = ctx.launches
     sync_all()
     infos, kernel_ms = [], []
@@ -771,7 +803,7 @@ def run_b200_dist(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", "--problem-size", dest="n", type=int, default=10_000_000)

@@ -39,6 +39,9 @@ def pytest_collection_modifyitems(config, items):
     ok, why = _device_ready()
     if ok:
         return
+    if os.path.exists("/dev/nvidia0") or os.path.exists("/dev/nvidiactl"):
+        # a GPU box: a library that does not load is a failure, never a skip
+        raise pytest.UsageError("CUDA device present but the native library is unusable: " + why)
     skip = pytest.mark.skip(reason="no usable CUDA device / library: " + why)
     for it in gpu_items:
         it.add_marker(skip)
