@@ -191,25 +191,48 @@ def host_threads():
     return t
 
 
-def cpu_reference_run(n, iters, steps, warmup, pattern, kappa):
-    """The reference's CPU path, restated by oracle/ (scipy SuperLU for
-    AugmentedSystem, numpy level-1, scipy csr_matvec): factorisation outside
-    the timed region, ``steps`` forced-iteration solves inside."""
+def reference_l1():
+    """The reference's own ``projections`` / ``projected_cg`` from the offline
+    install under baseline/_ref (scripts/install_reference.sh; it travels to the
+    GPU box with the snapshot), else the oracle port.  Returns
+    ``(kind, build_projectors, projected_cg)``."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isfile(os.path.join(ref, "ipsolver", "_large_scale_constrained", "qp_subproblem.py")):
+        try:
+            if ref not in sys.path:
+                sys.path.insert(0, ref)
+            import importlib
+            rp = importlib.import_module("ipsolver._large_scale_constrained.projections")
+            rq = importlib.import_module("ipsolver._large_scale_constrained.qp_subproblem")
+            return ("reference", lambda A: rp.projections(A, "AugmentedSystem"), rq.projected_cg)
+        except Exception as exc:          # broken install: say so, use the port
+            print("bench: baseline/_ref unusable (%r), timing the oracle port" % (exc,),
+                  file=sys.stderr)
     import oracle
+    return ("port", oracle.build_projectors, oracle.eqp_projected_cg)
+
+
+def cpu_reference_run(n, iters, steps, warmup, pattern, kappa):
+    """The reference's CPU path -- the UNMODIFIED reference from baseline/_ref
+    when it is installed (``kind`` "reference": its ``projections(A,
+    'AugmentedSystem')`` = scipy SuperLU, its ``projected_cg``), else the
+    oracle's restatement (``kind`` "port"): factorisation outside the timed
+    region, ``steps`` forced-iteration solves inside."""
     from ipsolver_b200 import synthetic
+    kind, build, pcg = reference_l1()
     H, A, c, b = synthetic.make_qp(n, pattern, kappa, seed=0)
     t0 = time.perf_counter()
-    Z, LS, Y = oracle.build_projectors(A)
+    Z, LS, Y = build(A)
     t_factor = time.perf_counter() - t0
     for _ in range(warmup):
-        oracle.eqp_projected_cg(H, c, Z, Y, b, tol=1e-30, max_iter=iters)
+        pcg(H, c, Z, Y, b, tol=1e-30, max_iter=iters)
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):
-        _, info = oracle.eqp_projected_cg(H, c, Z, Y, b, tol=1e-30, max_iter=iters)
+        _, info = pcg(H, c, Z, Y, b, tol=1e-30, max_iter=iters)
         done += info["niter"]
     dt = time.perf_counter() - t0
-    return done / dt, dt, t_factor
+    return done / dt, dt, t_factor, kind
 
 
 def solve_problem(n, pattern="window", kappa=10.0):
@@ -280,14 +303,15 @@ def run_reference(args):
     if rank != 0:
         return
     n_s = args.cpu_n
-    its, dt, t_factor = cpu_reference_run(n_s, args.iters, args.steps, args.warmup,
-                                          args.pattern, args.kappa)
-    sample = ("oracle port of the reference path (scipy SuperLU AugmentedSystem + numpy), "
+    its, dt, t_factor, kind = cpu_reference_run(n_s, args.iters, args.steps, args.warmup,
+                                                args.pattern, args.kappa)
+    sample = (("the UNMODIFIED reference from baseline/_ref (projections(A, 'AugmentedSystem') = "
+               "scipy SuperLU, its own projected_cg), " if kind == "reference" else
+               "oracle port of the reference path (scipy SuperLU AugmentedSystem + numpy), ") +
               "n=%d m=%d window A, %d steps x %d forced iterations in %.1f s; factorisation "
               "%.1f s outside the timed region; SuperLU factor / solve, csr_matvec and the "
               "numpy loops are single-threaded (cores = 1), only BLAS dot / norm may use "
-              "blas_threads"
-              % (n_s, n_s // 2, args.steps, args.iters, dt, t_factor))
+              "blas_threads") % (n_s, n_s // 2, args.steps, args.iters, dt, t_factor)
     ran = argparse.Namespace(**vars(args))
     ran.n = n_s
     line = {
@@ -304,7 +328,7 @@ def run_reference(args):
                                 "windowed pattern; NOT a measurement"},
         "cpu_baseline": {"value": its, "unit": UNIT, "cores": 1,
                          "blas_threads": host_threads(),
-                         "kind": "port", "sample": sample, "host_cpus": os.cpu_count()},
+                         "kind": kind, "sample": sample, "host_cpus": os.cpu_count()},
         "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -561,11 +585,12 @@ def run_b200(args):
     # ---- CPU baseline on a bounded sample (rank 0, N=1), and the GPU on that sample
     cpu, ref_cfg = None, None
     if not args.no_cpu:
-        its, dt, t_factor = cpu_reference_run(args.cpu_n, args.iters, args.cpu_steps, 0,
-                                              args.pattern, args.kappa)
+        its, dt, t_factor, kind = cpu_reference_run(args.cpu_n, args.iters, args.cpu_steps, 0,
+                                                    args.pattern, args.kappa)
         cpu = {"value": its, "unit": UNIT, "cores": 1, "blas_threads": host_threads(),
-               "kind": "port",
-               "sample": "oracle (scipy SuperLU AugmentedSystem + numpy) on the same workload "
+               "kind": kind,
+               "sample": ("the unmodified reference (baseline/_ref" if kind == "reference"
+                          else "oracle (port") + "; scipy SuperLU AugmentedSystem + numpy) on the same workload "
                          "at n=%d (the reference cannot factorise n=%d: SuperLU fails, "
                          "profiles/r3_reference_n1e7.txt): %d steps x %d forced iterations, "
                          "%.1f s timed + %.1f s factorisation; value is the MEASURED it/s at "
