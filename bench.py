@@ -247,11 +247,16 @@ def solve_problem(n, pattern="window", kappa=10.0):
 
 def end_to_end_solve(n, hot_path=None):
     import ipsolver_b200 as ipb
+    from threadpoolctl import threadpool_limits
     args, A, b = solve_problem(n)
-    t0 = time.perf_counter()
-    res = ipb.minimize_constrained(*args, ipb.LinearConstraint(A, ("equals", b)),
-                                   method='equality_constrained_sqp', hot_path=hot_path)
-    dt = time.perf_counter() - t0
+    # host BLAS threads as in the run that produced the reference record (8): the tail of this
+    # xtol-terminated run hangs on round-off in the host's dot / norm, for the reference as well
+    # (profiles/r5_host_threads.txt)
+    with threadpool_limits(limits=8):
+        t0 = time.perf_counter()
+        res = ipb.minimize_constrained(*args, ipb.LinearConstraint(A, ("equals", b)),
+                                       method='equality_constrained_sqp', hot_path=hot_path)
+        dt = time.perf_counter() - t0
     return {"n": n, "m": n // 2, "seconds": dt, "niter": int(res.niter),
             "cg_niter": int(res.cg_niter), "nfev": int(res.nfev), "status": int(res.status),
             "optimality": float(res.optimality), "fun": float(res.fun),

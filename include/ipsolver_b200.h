@@ -221,7 +221,14 @@ int ipb_modified_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *b,
  * c_t, the shifted bounds, d) are never uploaded again; the scalars of the
  * iteration are left to the host on the downloaded d, H d, A d (Ad may be NULL
  * when m = 0).  ipb_sqp_multipliers: v = -LS c, ||c + A'v||_inf (:227, :238);
- * its c becomes the resident gradient of the following steps. */
+ * its c becomes the resident gradient of the following steps.
+ * Row-partitioned contexts (ipb_comm_init): the same three calls, made by every
+ * rank with ITS OWN BLOCKS of c, b, lb, ub, dn, d, Hd, Ad, v (lengths = the
+ * projector's own n, m); products exchange ghosts and the solves reduce their
+ * scalars across the ranks inside the kernels.  ipb_sqp_multipliers then
+ * returns the rank's share of ||c + A'v||_inf -- the caller takes the maximum
+ * over the ranks.  ipb_modified_dogleg / ipb_projected_cg with host vectors stay
+ * single-GPU (use these or the *_dev entry points). */
 int ipb_sqp_normal_step(ipb_ctx *ctx, ipb_proj *P, const double *c, const double *b,
                         double normal_radius, const double *lb, const double *ub,
                         int bounds_changed, double box_factor, double *dn, ipb_proj_info *info);
@@ -239,6 +246,12 @@ int ipb_box_sphere_intersections(ipb_ctx *ctx, int64_t n, const double *z,
                                  const double *d, const double *lb, const double *ub,
                                  double trust_radius, int entire_line, double *ta,
                                  double *tb, int *intersect);
+/* The same on device vectors.  On a row-partitioned context the vectors are
+ * the rank's own blocks and the interval is reduced over the ranks inside the
+ * kernel (every rank gets the same ta, tb, intersect). */
+int ipb_box_sphere_intersections_dev(ipb_ctx *ctx, const ipb_vec *z, const ipb_vec *d,
+                                     const ipb_vec *lb, const ipb_vec *ub, double trust_radius,
+                                     int entire_line, double *ta, double *tb, int *intersect);
 
 /* ---- row-partitioned multi-GPU runs (one process per GPU) ---------------- */
 /* The reference is single-process (no communication

@@ -102,6 +102,7 @@ struct ipb_ctx {
     // vectors of the fused SQP step (ipb_sqp_step): resident across outer iterations
     double *step = nullptr;
     size_t step_len = 0;
+    double *step_nv[16] = {nullptr}, *step_mv[8] = {nullptr};   // the step's n- / m-vectors
     int64_t step_n = -1, step_m = -1;
     bool step_has_c = false, step_has_b = false, step_has_box = false;
     double *glue_partials = nullptr, *glue_sums = nullptr;
@@ -1349,7 +1350,8 @@ static int run_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *db, double trust_
     const int64_t n = P->n, m = P->m;
     const bool box = dlb && dub;
     const size_t ns = vstride(n), mstr = vstride(m);
-    CHECK(ensure_ws(ctx, 7 * ns + mstr));
+    if (ctx->size == 1) CHECK(ensure_ws(ctx, 7 * ns + mstr));
+    else CHECK(dist_workspace(ctx));        // arena vectors: products exchange their ghosts
     DoglegArgs a;
     memset(&a, 0, sizeof a);
     a.P = proj_view(P); a.S = sync_view(ctx);
@@ -1357,9 +1359,15 @@ static int run_dogleg(ipb_ctx *ctx, ipb_proj *P, const double *db, double trust_
     else { a.Araw = csr_view(P->A); a.Atraw = csr_view_t(P->A); }
     a.n = (int)n; a.m = (int)m; a.b = db; a.lb = box ? dlb : nullptr; a.ub = box ? dub : nullptr;
     a.has_box = box; a.radius = trust_radius;
-    double *w = ctx->ws;
-    a.newton = w; a.cauchy = w + ns; a.g = w + 2 * ns; a.x1 = w + 3 * ns; a.x2 = w + 4 * ns;
-    a.out = w + 5 * ns; a.mtmp = w + 7 * ns;
+    if (ctx->size == 1) {
+        double *w = ctx->ws;
+        a.newton = w; a.cauchy = w + ns; a.g = w + 2 * ns; a.x1 = w + 3 * ns; a.x2 = w + 4 * ns;
+        a.out = w + 5 * ns; a.mtmp = w + 7 * ns;
+    } else {
+        double **d = ctx->dws_n;
+        a.newton = d[0]; a.cauchy = d[1]; a.g = d[2]; a.x1 = d[3]; a.x2 = d[4]; a.out = d[5];
+        a.mtmp = ctx->dws_m;
+    }
     a.result = (ProjArgs::Result *)ctx->d_result;
     float ms = 0.f;
     CHECK(launch_coop(ctx, k_dogleg, a, proj_grid(ctx, P), &ms));
@@ -1429,7 +1437,6 @@ enum { SV_C = 0, SV_LB, SV_UB, SV_LBN, SV_UBN, SV_LBT, SV_UBT, SV_DN, SV_CT, SV_
 enum { SM_B = 0, SM_LIN, SM_ZERO, SM_V, SM_MCOUNT };
 
 static int ensure_step(ipb_ctx *ctx, int64_t n, int64_t m) {
-    SINGLE_GPU_ONLY(ctx);
     if (!ctx->glue_partials) {
         CHECK(dalloc(ctx, &ctx->glue_partials, 3 * 1024));
         CHECK(dalloc(ctx, &ctx->glue_sums, 3 * 8));
@@ -1437,23 +1444,35 @@ static int ensure_step(ipb_ctx *ctx, int64_t n, int64_t m) {
         CU(ctx, cudaMemset(ctx->glue_counter, 0, sizeof(unsigned)));
     }
     if (ctx->step_n == n && ctx->step_m == m) return IPB_OK;
-    const size_t need = SV_NCOUNT * vstride(n) + SM_MCOUNT * vstride(m);
-    if (ctx->step_len < need) {
-        cudaFree(ctx->step);
-        ctx->step = nullptr; ctx->step_len = 0;
-        CHECK(dalloc(ctx, &ctx->step, need));
-        ctx->step_len = need;
+    static_assert(SV_NCOUNT <= 16 && SM_MCOUNT <= 8, "step vector tables");
+    if (ctx->size > 1) {
+        // row-partitioned: n, m are the rank's own lengths; every vector comes from the
+        // symmetric arena (same order on every rank) so that products find its ghost zones
+        if (ctx->step_n >= 0)
+            IPB_FAIL(ctx, IPB_ERR_INVALID, "a row-partitioned context serves one problem");
+        if (n != ctx->own[0] || m != ctx->own[1])
+            IPB_FAIL(ctx, IPB_ERR_INVALID, "SQP step: the projector does not belong to this partition");
+        for (int k = 0; k < SV_NCOUNT; ++k) CHECK(valloc(ctx, &ctx->step_nv[k], n));
+        for (int k = 0; k < SM_MCOUNT; ++k) CHECK(valloc(ctx, &ctx->step_mv[k], m));
+    } else {
+        const size_t need = SV_NCOUNT * vstride(n) + SM_MCOUNT * vstride(m);
+        if (ctx->step_len < need) {
+            cudaFree(ctx->step);
+            ctx->step = nullptr; ctx->step_len = 0;
+            CHECK(dalloc(ctx, &ctx->step, need));
+            ctx->step_len = need;
+        }
+        for (int k = 0; k < SV_NCOUNT; ++k) ctx->step_nv[k] = ctx->step + (size_t)k * vstride(n);
+        for (int k = 0; k < SM_MCOUNT; ++k)
+            ctx->step_mv[k] = ctx->step + SV_NCOUNT * vstride(n) + (size_t)k * vstride(m);
     }
     ctx->step_n = n; ctx->step_m = m;
     ctx->step_has_c = ctx->step_has_b = ctx->step_has_box = false;
-    double *zero = ctx->step + SV_NCOUNT * vstride(n) + SM_ZERO * vstride(m);
-    CU(ctx, cudaMemsetAsync(zero, 0, vstride(m) * 8, ctx->stream));
+    if (m) CU(ctx, cudaMemsetAsync(ctx->step_mv[SM_ZERO], 0, (size_t)m * 8, ctx->stream));
     return IPB_OK;
 }
-static inline double *step_n(ipb_ctx *ctx, int k) { return ctx->step + (size_t)k * vstride(ctx->step_n); }
-static inline double *step_m(ipb_ctx *ctx, int k) {
-    return ctx->step + SV_NCOUNT * vstride(ctx->step_n) + (size_t)k * vstride(ctx->step_m);
-}
+static inline double *step_n(ipb_ctx *ctx, int k) { return ctx->step_nv[k]; }
+static inline double *step_m(ipb_ctx *ctx, int k) { return ctx->step_mv[k]; }
 
 extern "C" int ipb_sqp_normal_step(ipb_ctx *ctx, ipb_proj *P, const double *c, const double *b,
                                    double normal_radius, const double *lb, const double *ub,
@@ -1519,7 +1538,8 @@ extern "C" int ipb_sqp_tangential_step(ipb_ctx *ctx, const ipb_hess *H, ipb_proj
     CHECK(run_hess(ctx, H, step_n(ctx, SV_D), step_n(ctx, SV_HD)));
     if (n) CU(ctx, cudaMemcpyAsync(Hd, step_n(ctx, SV_HD), (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (m > 0 && Ad) {
-        CHECK(run_matvec(ctx, csr_view(P->A), step_n(ctx, SV_D), step_m(ctx, SM_LIN)));
+        CHECK(run_matvec(ctx, P->parts ? csr_view(P->pA_raw) : csr_view(P->A), step_n(ctx, SV_D),
+                         step_m(ctx, SM_LIN)));
         CU(ctx, cudaMemcpyAsync(Ad, step_m(ctx, SM_LIN), (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1578,6 +1598,29 @@ extern "C" int ipb_box_sphere_intersections(ipb_ctx *ctx, int64_t n, const doubl
     a.has_box = box; a.line = entire_line; a.radius = trust_radius;
     a.result = (IntersectArgs::Result *)ctx->d_result;
     CHECK(launch_coop(ctx, k_intersect, a, grid_for(ctx, n), nullptr));
+    IntersectArgs::Result *h = (IntersectArgs::Result *)ctx->h_result;
+    CU(ctx, cudaMemcpyAsync(h, ctx->d_result, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *ta = h->ta; *tb = h->tb; *intersect = h->hit;
+    return IPB_OK;
+}
+
+// The same on device vectors (row-partitioned contexts: the rank's own blocks; the
+// interval is reduced over the ranks inside the kernel).
+extern "C" int ipb_box_sphere_intersections_dev(ipb_ctx *ctx, const ipb_vec *z, const ipb_vec *d,
+                                                const ipb_vec *lb, const ipb_vec *ub,
+                                                double trust_radius, int entire_line, double *ta,
+                                                double *tb, int *intersect) {
+    if (!ctx || !z || !d || !ta || !tb || !intersect || z->len != d->len) return IPB_ERR_INVALID;
+    const bool box = lb && ub;
+    if (box && (lb->len != z->len || ub->len != z->len)) return IPB_ERR_INVALID;
+    IntersectArgs a;
+    memset(&a, 0, sizeof a);
+    a.S = sync_view(ctx); a.n = (int)z->len; a.z = z->d; a.d = d->d;
+    a.lb = box ? lb->d : nullptr; a.ub = box ? ub->d : nullptr;
+    a.has_box = box; a.line = entire_line; a.radius = trust_radius;
+    a.result = (IntersectArgs::Result *)ctx->d_result;
+    CHECK(launch_coop(ctx, k_intersect, a, grid_for(ctx, std::max<int64_t>(z->len, 1) * 4), nullptr));
     IntersectArgs::Result *h = (IntersectArgs::Result *)ctx->h_result;
     CU(ctx, cudaMemcpyAsync(h, ctx->d_result, sizeof(*h), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

@@ -103,6 +103,8 @@ PROTOTYPES = {
     "ipb_box_sphere_intersections": (C.c_int, [_P, _I64, _D, _D, _D, _D,
                                                C.c_double, C.c_int, _D, _D,
                                                C.POINTER(C.c_int)]),
+    "ipb_box_sphere_intersections_dev": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, C.c_int, _D, _D,
+                                                   C.POINTER(C.c_int)]),
     "ipb_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_I64), C.POINTER(_I64),
                                 C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64),
                                 C.POINTER(_I64), _I64, _I64, _P]),

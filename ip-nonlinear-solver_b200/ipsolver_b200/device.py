@@ -255,6 +255,10 @@ class DeviceProjector:
     """Z, LS, Y of ``projections.py:290`` with (A A')^-1 applied on the device
     (banded direct solve or CG).  Holds the device copy of A (and A')."""
 
+    # row-partitioned ranks must all take the same "is there a box" decision: a rank whose
+    # own block happens to have no finite bound still runs the box passes (distributed.py)
+    keep_given_bounds = False
+
     def __init__(self, ctx, A, orth_tol=1e-12, max_refin=3, inner_rtol=1e-13,
                  inner_maxit=1000, aat_mode=0, band=(0, 0, 0)):
         self.ctx = ctx
@@ -360,7 +364,10 @@ class DeviceProjector:
         for :meth:`sqp_tangential_step` (``None``: unchanged since the last call)."""
         c = None if c is None else f64(c, self.n)
         b = None if b is None else f64(b, self.m)
-        lb, ub = _bounds(lb, ub, self.n)
+        if self.keep_given_bounds and lb is not None and ub is not None:
+            lb, ub = f64(lb, self.n), f64(ub, self.n)     # the box decision is the caller's (global)
+        else:
+            lb, ub = _bounds(lb, ub, self.n)
         dn = self.ctx.empty(self.n)
         info = ProjInfo()
         self.ctx.check(self.ctx.lib.ipb_sqp_normal_step(

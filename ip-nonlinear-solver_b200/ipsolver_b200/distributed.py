@@ -320,7 +320,9 @@ class DistSolver:
         own = I64x2(self.part.own_len(rank, 0), self.part.own_len(rank, 1))
         own_max = I64x2(self.part.own_max(0), self.part.own_max(1))
         stride = [glo[k] + own_max[k] + ghi[k] + 64 for k in (0, 1)]
-        arena = 8 * (24 * stride[0] + 16 * stride[1]) + (1 << 20)
+        # solver workspaces (7 n + 1 m), projector (1 n + 7 m), the SQP step (13 n + 4 m), helper
+        # vectors of the outer loop and the caller's own: room for 48 n- and 32 m-vectors
+        arena = 8 * (48 * stride[0] + 32 * stride[1]) + (1 << 20)
         handle = (C.c_char * 64)()
         mine = parts["ghosts"]
         ctx.check(lib.ipb_comm_init(ctx.h, self.rank, self.size, own, own_max, I64x2(*glo),
@@ -399,9 +401,156 @@ class DistSolver:
         dist.all_gather_object(pieces, np.asarray(x_local), group=self.group)
         return np.concatenate(pieces)
 
+    def allgather(self, local, space=N_SPACE):
+        """The full vector from the ranks' own blocks, on every rank (blocks padded
+        to the largest one; gloo moves host tensors, nccl device tensors)."""
+        import torch
+        import torch.distributed as dist
+        cap = max(self.part.own_max(space), 1)
+        buf = np.zeros(cap)
+        buf[:len(local)] = local
+        t = torch.from_numpy(buf)
+        if dist.get_backend(self.group) == "nccl":
+            t = t.cuda(self.ctx.device)
+        out = [torch.empty_like(t) for _ in range(self.size)]
+        dist.all_gather(out, t, group=self.group)
+        off = self.part.offsets(space)
+        return np.concatenate([o.cpu().numpy()[:off[g + 1] - off[g]] for g, o in enumerate(out)])
 
-class _ProjHandle:
-    """Minimal projector object for the *_dev calls (holds ctx and handle)."""
+    def allmax(self, value):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([float(value)], dtype=torch.float64)
+        if dist.get_backend(self.group) == "nccl":
+            t = t.cuda(self.ctx.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
+    def _scratch(self, space, k):
+        """Helper device vectors of the outer loop (allocated once, in the same
+        order on every rank: they live in the symmetric arena)."""
+        pool = self.__dict__.setdefault("_scratch_pool", {})
+        for j in range(k + 1):                       # same allocation order on every rank
+            if (space, j) not in pool:
+                pool[(space, j)] = self.vector(space=space)
+        return pool[(space, k)]
+
+    def apply_map(self, which, x_full):
+        """``Z.dot`` / ``LS.dot`` / ``Y.dot`` on a full host vector (every rank
+        passes the same one and gets the full result)."""
+        from .device import ProjInfo
+        lib, ctx = self.ctx.lib, self.ctx
+        fn, sin, sout = {"Z": (lib.ipb_proj_null_space_dev, N_SPACE, N_SPACE),
+                         "LS": (lib.ipb_proj_least_squares_dev, N_SPACE, M_SPACE),
+                         "Y": (lib.ipb_proj_row_space_dev, M_SPACE, N_SPACE)}[which]
+        vin = self._scratch(sin, 0)
+        vout = self._scratch(sout, 1)
+        vin.upload(self.local(x_full, sin))
+        info = ProjInfo()
+        ctx.check(fn(ctx.h, self.proj.h, vin.h, vout.h, C.byref(info)))
+        return self.allgather(vout.download(), sout)
+
+    def box_intersections(self, z, d, lb, ub, entire_line=False):
+        """``box_intersections`` (qp_subproblem.py:152-234) on full host vectors,
+        evaluated block-wise on the ranks and reduced inside the kernel."""
+        lib, ctx = self.ctx.lib, self.ctx
+        vs = [self._scratch(N_SPACE, k) for k in range(4)]
+        for v, full in zip(vs, (z, d, lb, ub)):
+            v.upload(self.local(np.asarray(full, dtype=np.float64), N_SPACE))
+        ta, tb, hit = C.c_double(), C.c_double(), C.c_int()
+        ctx.check(lib.ipb_box_sphere_intersections_dev(
+            ctx.h, vs[0].h, vs[1].h, vs[2].h, vs[3].h, float("inf"), int(bool(entire_line)),
+            C.byref(ta), C.byref(tb), C.byref(hit)))
+        return ta.value, tb.value, bool(hit.value)
+
+    def hot_path(self, H=None, A=None):
+        """The L1 functions of ``equality_constrained_sqp`` for a row-partitioned
+        problem with CONSTANT matrices (a QP: BASELINE configs 2 and 5): pass it
+        as ``minimize_constrained(..., hot_path=solver.hot_path(H, A))`` on every
+        rank.  Every rank runs the same host loop on full host vectors (SPMD, the
+        callbacks are the user's); each device step works on the rank's own
+        blocks -- ``ipb_sqp_normal_step`` / ``ipb_sqp_tangential_step`` /
+        ``ipb_sqp_multipliers`` on the partitioned context -- and the results are
+        all-gathered, so all scalars are the numpy expressions of the single-GPU
+        loop on identical data: same decisions on every rank, and the same
+        iteration path as one GPU.  ``H`` / ``A`` (optional): the global matrices
+        the solver was built from, to reject a problem whose matrices change."""
+        from types import SimpleNamespace
+        from .equality_constrained_sqp import ZETA_NORMAL, BOX_NORMAL
+        solver = self
+
+        class _Map:
+            def __init__(self, which, shape):
+                self.which, self.shape, self.projector = which, shape, solver.proj
+
+            def dot(self, x):
+                return solver.apply_map(self.which, np.asarray(x, dtype=np.float64))
+
+        class _Hessian:
+            """Marker for the partitioned (constant) Hessian; ``dot`` for callers
+            that want a product on the host is not offered on purpose."""
+            def __init__(self, n, terms):
+                self.shape, self.terms = (n, n), terms
+
+        def same_matrix(X, ref):
+            if ref is None or X is ref:
+                return True
+            X, ref = sps.csr_matrix(X), sps.csr_matrix(ref)
+            return (X.shape == ref.shape and X.nnz == ref.nnz
+                    and np.array_equal(X.indptr, ref.indptr)
+                    and np.array_equal(X.indices, ref.indices) and np.array_equal(X.data, ref.data))
+
+        def projections(A_now, method=None):
+            if not same_matrix(A_now, A):
+                raise NotImplementedError("row-partitioned runs take a constant Jacobian "
+                                          "(linear constraints); this one changed")
+            n, m = solver.part.n, solver.part.m
+            return _Map("Z", (n, n)), _Map("LS", (m, n)), _Map("Y", (n, m))
+
+        def hessian(n, terms):
+            if len(terms) != 1 or not same_matrix(terms[0], H):
+                raise NotImplementedError("row-partitioned runs take a constant Hessian (a QP)")
+            return _Hessian(n, terms)
+
+        def fused_step(Hop, Z, c, b, radius, lb, ub, bounds_changed):
+            loc = solver.local
+            dn = solver.allgather(solver.proj.sqp_normal_step(
+                None if c is None else loc(c, N_SPACE), None if b is None else loc(b, M_SPACE),
+                ZETA_NORMAL * radius, None if lb is None else loc(lb, N_SPACE),
+                None if ub is None else loc(ub, N_SPACE), bounds_changed, BOX_NORMAL), N_SPACE)
+            radius_t = np.sqrt(radius**2 - np.linalg.norm(dn)**2)
+            d, Hd, Ad, cg_info = solver.proj.sqp_tangential_step(solver.H, radius_t)
+            return (dn, solver.allgather(d, N_SPACE), solver.allgather(Hd, N_SPACE),
+                    solver.allgather(Ad, M_SPACE), cg_info)
+
+        def fused_multipliers(Z, c):
+            v, opt = solver.proj.sqp_multipliers(solver.local(c, N_SPACE))
+            return solver.allgather(v, M_SPACE), solver.allmax(opt)
+
+        def unavailable(*a, **k):
+            raise NotImplementedError("the row-partitioned hot path runs the fused SQP step only")
+
+        return SimpleNamespace(projections=projections, hessian=hessian, fused_step=fused_step,
+                               fused_multipliers=fused_multipliers,
+                               can_fuse=lambda Hop: isinstance(Hop, _Hessian),
+                               box_intersections=solver.box_intersections,
+                               projected_cg=unavailable, modified_dogleg=unavailable,
+                               jac_dot=unavailable, jac_tdot=unavailable)
+
+
+from .device import DeviceProjector as _DeviceProjector  # noqa: E402
+
+
+class _ProjHandle(_DeviceProjector):
+    """Projector of one rank (created by ``ipb_proj_create_parts``): the *_dev
+    calls and the SQP-step calls of :class:`DeviceProjector` on the rank's own
+    blocks (``n``, ``m`` are the own lengths)."""
+
+    keep_given_bounds = True
 
     def __init__(self, ctx, h, m, n):
-        self.ctx, self.h, self.m, self.n = ctx, h, m, n
+        self.ctx, self.h, self.m, self.n = ctx, h, int(m), int(n)
+        self.A = None
+        self.last_info = None
+        self.totals = dict(inner_iters=0, n_solves=0, n_refinements=0, applies=0,
+                           n_fallbacks=0)

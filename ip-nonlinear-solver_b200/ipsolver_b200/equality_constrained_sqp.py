@@ -134,7 +134,8 @@ def equality_constrained_sqp(fun_and_constr, grad_and_jac, lagr_hess,
         if need_hessian:
             H = lagr_hess(x, v)
             state.nhev += 1
-        use_fused = fused and getattr(H, "device", None) is not None
+        use_fused = fused and (hp.can_fuse(H) if hasattr(hp, "can_fuse")
+                               else getattr(H, "device", None) is not None)
         if use_fused:
             dn, d, Hd, Ad, cg_info = hp.fused_step(H, Z, c if c_up else None, b if b_up else None,
                                                    radius, lb if bounded else None,

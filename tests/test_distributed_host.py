@@ -194,3 +194,102 @@ def test_band_window_of_a_rank_solves_like_the_global_factor(size):
         v_loc = spla.spsolve(M[w0:w1, w0:w1].tocsc(), rhs[w0:w1])
         err = np.linalg.norm(v_loc[m0 - w0:m1 - w0] - v_ref[m0:m1]) / np.linalg.norm(v_ref[m0:m1])
         assert err < 1e-13
+
+
+SQP_WORKER = r'''
+import os, sys, numpy as np
+sys.path[:0] = [%r, %r]
+import torch.distributed as dist
+import oracle
+import ipsolver_b200 as ipb
+from ipsolver_b200 import synthetic, distributed as D
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% sys.argv[1],
+                        rank=int(sys.argv[2]), world_size=2)
+rank = dist.get_rank()
+n = 400
+H, A, q, b = synthetic.make_qp(n, "window", 10.0, seed=0)
+m = A.shape[0]
+
+class FakeProj:
+    """Stands in for the device: every call gathers its block inputs into full
+    vectors (as the kernels see them through ghosts and reductions), computes
+    with the oracle on the whole problem and hands back the rank's own block."""
+    def __init__(self, S):
+        self.S = S
+        self.Z, self.LS, self.Y = oracle.build_projectors(A)
+        self.c = self.b = self.lb = self.ub = None
+    def own(self, v, space):
+        return self.S.local(v, space)
+    def sqp_normal_step(self, c, b, radius, lb, ub, bounds_changed, box_factor):
+        if c is not None: self.c = self.S.allgather(c, 0)
+        if b is not None: self.b = self.S.allgather(b, 1)
+        if lb is not None and bounds_changed:
+            self.lb, self.ub = self.S.allgather(lb, 0), self.S.allgather(ub, 0)
+        lbn = np.full(n, -np.inf) if self.lb is None else box_factor * self.lb
+        ubn = np.full(n, np.inf) if self.ub is None else box_factor * self.ub
+        self.dn = oracle.dogleg_normal_step(A, self.Y, self.b, radius, lbn, ubn)
+        return self.own(self.dn, 0)
+    def sqp_tangential_step(self, Hdev, radius_t):
+        assert Hdev == "H of the ranks"
+        lb = np.full(n, -np.inf) if self.lb is None else self.lb
+        ub = np.full(n, np.inf) if self.ub is None else self.ub
+        dt, info = oracle.eqp_projected_cg(H, H.dot(self.dn) + self.c, self.Z, self.Y, np.zeros(m),
+                                           radius_t, lb - self.dn, ub - self.dn)
+        d = self.dn + dt
+        return self.own(d, 0), self.own(H.dot(d), 0), self.own(A.dot(d), 1), info
+    def sqp_multipliers(self, c):
+        self.c = self.S.allgather(c, 0)
+        v = -self.LS.dot(self.c)
+        r = np.abs(self.c + A.T.dot(v))
+        n0, n1 = self.S.part.own(rank, 0)
+        return self.own(v, 1), float(r[n0:n1].max())      # the rank's share of the inf-norm
+
+S = object.__new__(D.DistSolver)
+S.rank, S.size, S.group = rank, 2, dist.group.WORLD
+S.part = D.RowPartition(n, m, 2)
+S.ctx = type("Ctx", (), {"device": 0})()
+S.H = "H of the ranks"
+S.proj = FakeProj(S)
+# the second-order correction's helpers (Y.dot, box_intersections) go to the device too
+S.apply_map = lambda which, x: {"Z": S.proj.Z, "LS": S.proj.LS, "Y": S.proj.Y}[which].dot(x)
+S.box_intersections = oracle.segment_box
+# allgather / allmax plumbing
+x = np.arange(n, dtype=float)
+assert np.array_equal(S.allgather(S.local(x, 0), 0), x)
+assert np.array_equal(S.allgather(S.local(x[:m], 1), 1), x[:m])
+assert S.allmax(float(rank)) == 1.0
+args = (lambda x: 0.5 * x.dot(H.dot(x)) + q.dot(x), np.zeros(n), lambda x: H.dot(x) + q, lambda x: H)
+con = ipb.LinearConstraint(A, ("equals", b))
+res = ipb.minimize_constrained(*args, con, method='equality_constrained_sqp', hot_path=S.hot_path(H, A))
+ref = ipb.minimize_constrained(*args, con, method='equality_constrained_sqp',
+                               hot_path=oracle.host_hot_path())
+assert (res.niter, res.cg_niter, res.nfev, res.status) == (ref.niter, ref.cg_niter, ref.nfev, ref.status), \
+    ((res.niter, res.cg_niter, res.nfev, res.status), (ref.niter, ref.cg_niter, ref.nfev, ref.status))
+assert np.array_equal(res.x, ref.x) and np.array_equal(res.v, ref.v)
+assert res.optimality == ref.optimality
+# a problem whose matrices are not the solver's is refused, not silently mis-solved
+try:
+    S.hot_path(H, A).projections(A * 2.0)
+    raise SystemExit("changed Jacobian accepted")
+except NotImplementedError:
+    pass
+dist.barrier()
+print("rank", rank, "ok", res.niter, res.cg_niter)
+'''
+
+
+def test_row_partitioned_sqp_loop_world_size_2(tmp_path):
+    """``DistSolver.hot_path()`` under the SQP loop, two gloo ranks, the device
+    replaced by the oracle working on gathered vectors: block slicing,
+    all-gathers, the global box / fuse decisions and the replicated host loop
+    reproduce the single-process run exactly."""
+    script = tmp_path / "sqp_worker.py"
+    script.write_text(SQP_WORKER % (ROOT, os.path.join(ROOT, "ip-nonlinear-solver_b200")))
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), port, str(r)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o[-3000:]
+        assert "rank %d ok" % r in o

@@ -42,7 +42,7 @@ def _sample_err(res, gold, name):
     return ex, ev, abs(np.linalg.norm(res.x) - nx) / nx, abs(np.linalg.norm(res.v) - nv) / nv
 
 
-def test_config2_sqp_n1e6_matches_the_reference(api, gold):
+def test_config2_sqp_n1e6_matches_the_reference(api, gold, golden_host_threads):
     name = "eqp_window_1000000"
     niter, cg, status, nfev, opt, viol, fval, radius, t_ref = gold[name + "/scalars"]
     res = e2e_problems.LARGE_PROBLEMS[name](api)()

@@ -29,3 +29,18 @@ def test_two_ranks_match_single_gpu(pattern):
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count(" OK") >= 3 and "MISMATCH" not in out.stdout
+
+
+def test_two_ranks_run_the_sqp_loop_like_one_gpu():
+    """``DistSolver.hot_path()`` under ``equality_constrained_sqp``: dogleg,
+    projected CG, ``H d``, ``A d``, ``LS c`` and the second-order correction's
+    ``Y b`` / ``box_intersections`` on two row-partitioned GPUs reproduce the
+    single-GPU run (counts +-1, x and multipliers to 1e-8)."""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(29900 + os.getpid() % 300),
+           os.path.join(ROOT, "scripts", "dist_sqp_check.py"), "100000", "window"]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count(" OK") >= 2 and "MISMATCH" not in out.stdout
