@@ -436,6 +436,8 @@ def run_b200(args):
     rank = 0
     n, m = args.n, args.n // 2
     set_inner_options(inner_rtol=args.inner_rtol)
+    if args.band_chunk:
+        set_inner_options(band=(0, args.band_chunk, 0))     # tuning aid: rows per sweep chunk
     t0 = time.perf_counter()
     H, A, c, b = synthetic.make_qp(n, args.pattern, args.kappa, seed=0)
     t_gen = time.perf_counter() - t0
@@ -881,6 +883,8 @@ def main():
     ap.add_argument("--pattern", default="window")
     ap.add_argument("--kappa", type=float, default=1e4)
     ap.add_argument("--inner-rtol", type=float, default=1e-13)
+    ap.add_argument("--band-chunk", type=int, default=0,
+                    help="rows per chunk of the banded sweep (0: the library's rule)")
     ap.add_argument("--cpu-n", type=int, default=4_000_000)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
