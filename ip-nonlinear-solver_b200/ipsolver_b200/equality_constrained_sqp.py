@@ -11,9 +11,12 @@ goes to the device
 through ``ipsolver_b200``; user callbacks (``fun_and_constr``,
 ``grad_and_jac``, ``lagr_hess``) run on the host between those calls.
 
-``hot_path`` lets the CPU tests drive this loop with the oracle's routines to
-check the host logic against the reference's golden results without a GPU; the
-product never passes it.
+``hot_path`` is the object that supplies those functions: by default the
+single-GPU device path below; ``distributed.DistSolver.hot_path()`` for a
+row-partitioned run (every rank runs this loop on the same host vectors, each
+device step works on the rank's own blocks); the CPU tests pass the oracle's
+routines to check the host logic against the reference's golden results
+without a GPU.
 """
 from types import SimpleNamespace
 

@@ -246,8 +246,10 @@ def minimize_constrained(fun, x0, grad, hess, constraints=(), method=None, xtol=
                          gtol=1e-8, sparse_jacobian=None, options={}, callback=None,
                          max_iter=1000, verbose=0, hot_path=None):
     """Reference ``minimize_constrained`` (``_minimize_constrained.py:96``) for
-    Hessians given as matrices.  ``hot_path`` is for the CPU tests only (see
-    ``equality_constrained_sqp``)."""
+    Hessians given as matrices.  ``hot_path`` supplies the L1 functions the
+    loops call (default: the single-GPU device path;
+    ``DistSolver.hot_path()`` for a row-partitioned run; the CPU tests pass
+    the oracle's routines) -- it is not part of the reference's signature."""
     hp = hot_path or device_hot_path()
     x0 = np.atleast_1d(x0).astype(float)
     n_vars = x0.size
