@@ -700,7 +700,10 @@ def run_b200_dist(args):
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    gloo = dist.new_group(backend="gloo")
+    # setup-time collectives only; a bounded timeout so that a rank that failed in an extra leg
+    # (the SQP solve below) surfaces as an exception on its peers instead of a hang
+    import datetime
+    gloo = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=600))
     n, m = args.n, args.n // 2
     hashed = args.pattern == "hashed"
     t0 = time.perf_counter()
